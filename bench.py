@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- jacobi3d cells/s at 512^3 per GPU, radius 1, FP64 (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU arm (oracle port, all host cores)
+
+A "step" is one iteration of the reference driver's loop (bin/jacobi3d.cu:296-368): interior kernel
+|| halo exchange -> exterior slabs -> stream sync -> swap.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "jacobi3d_cells_per_s"
+UNIT = "cells/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--size", type=int, default=512, help="per-GPU cube edge (BASELINE: 512)")
+    p.add_argument("--dtype", default="f64", choices=["f32", "f64"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-overlap", action="store_true")
+    return p.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL,
+                text=True,
+            )
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "power_w_max": max(power) if power else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+class CpuJacobi:
+    """The oracle port of the same loop on one periodic 512^3 subdomain (C + OpenMP, oracle/stencil_oracle.c).
+    Used for `cpu_baseline` and for `--impl reference` (the reference has no runnable
+    CPU path; BASELINE.md 2a: the CPU baseline is this restatement)."""
+
+    def __init__(self, n: int, dtype):
+        from oracle import c_oracle as co
+        from oracle import geometry as g
+
+        self.co, self.g, self.n = co, g, n
+        self.r = g.Radius.face_edge_corner(1, 0, 0)
+        raw = g.raw_size((n, n, n), self.r)
+        self.cur = np.zeros(raw[::-1], dtype=dtype)
+        self.nxt = np.zeros(raw[::-1], dtype=dtype)
+        co.fill(self.cur, (1, 1, 1), (n, n, n), 0.5)
+        self.interior = g.get_interior((0, 0, 0), (n, n, n), self.r)
+        self.exterior = g.get_exterior((0, 0, 0), (n, n, n), self.r)
+        self.plan = g.plan_sends((1, 1, 1), {(0, 0, 0): (n, n, n)}, self.r)
+        self._mk()
+
+    def _mk(self):
+        self.copies = [
+            self.co.make_copies([(a, m["dst_pos"], a, m["src_pos"], m["ext"]) for m in self.plan]) for a in (self.cur, self.nxt)
+        ]
+        self.par = 0
+
+    def step(self):
+        co, n = self.co, self.n
+        cur, nxt = (self.cur, self.nxt) if self.par == 0 else (self.nxt, self.cur)
+        creg = ((0, 0, 0), (n, n, n))
+        co.jacobi_region(nxt, cur, (-1, -1, -1), *self.interior, *creg)
+        co.translate_many(*self.copies[self.par])
+        for lo, hi in self.exterior:
+            co.jacobi_region(nxt, cur, (-1, -1, -1), lo, hi, *creg)
+        self.par ^= 1
+
+    def current(self):
+        return self.cur if self.par == 0 else self.nxt
+
+
+def time_cpu(n, dtype, steps, warmup, budget_s=None):
+    from oracle import c_oracle as co
+
+    cj = CpuJacobi(n, dtype)
+    for _ in range(warmup):
+        cj.step()
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cj.step()
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s:
+            break
+    mean = float(np.mean(times))
+    return {"value": n**3 / mean, "ms_per_step": mean * 1e3, "steps": len(times), "cores": co.num_threads()}
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (see CpuJacobi)."""
+    if rank != 0:
+        return
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    n = args.size
+    res = time_cpu(n, dtype, args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": res["value"],
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": res["steps"],
+        "warmup": max(args.warmup, 1),
+        "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": args.dtype,
+        "data": "synthetic",
+        "config": {
+            "workload": f"jacobi3d {n}^3 radius-1 {args.dtype.upper()} (BASELINE configs[1]), one periodic subdomain on the host",
+            "note": "reference has no runnable CPU path (SURVEY.md fact 1); this is the oracle port: C + OpenMP restatement of bin/jacobi3d.cu:296-368",
+            "cpu": cpu_model(),
+        },
+        "cpu_baseline": {
+            "value": res["value"],
+            "unit": UNIT,
+            "cores": res["cores"],
+            "kind": "port",
+            "sample": f"{res['steps']} full iterations of {n}^3 (interior + 6-face periodic exchange + exterior)",
+        },
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as td
+
+    import stencil_b200 as sb
+    from stencil_b200.jacobi import Jacobi3D, jacobi_radius, scaled_size
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- stencil_b200 has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    L = sb.lib()
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    es = np.dtype(dtype).itemsize
+    n = args.size
+    ngpu = args.gpus
+    if world == 1 and ngpu > 1:
+        gpus = list(range(ngpu))  # one process driving N GPUs (the reference's 1 rank x N GPUs mode)
+    else:
+        gpus = [local]
+    X, Y, Z = scaled_size(n, n, n, ngpu)
+
+    dd = sb.DistributedDomain(X, Y, Z)
+    dd.set_gpus(gpus)
+    dd.set_radius(jacobi_radius())
+    h = dd.add_data(dtype, "d")
+    dd.realize()
+    jac = Jacobi3D(dd, h, overlap=not args.no_overlap)
+    jac.init(0.5)
+
+    def barrier():
+        for d in dd.domains():
+            sb._lib.check(L.sb_device_sync(d.gpu()))
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        jac.step()
+
+    # ---- device-resident timed region -------------------------------------------------------
+    cs0 = jac.streams[0]
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    launches0 = L.sb_launch_count()
+    t_wall0 = time.perf_counter()
+    ev_a.record(cs0)
+    for i in range(args.steps):
+        k0[i].record(cs0)
+        if jac.overlap:
+            jac.launch_interior()
+            k1[i].record(cs0)
+            dd.exchange()
+            jac.launch_exterior()
+        else:
+            dd.exchange()
+            jac.launch_whole()
+            k1[i].record(cs0)
+        for s in jac.streams:
+            s.synchronize()
+        dd.swap()
+    ev_b.record(cs0)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = L.sb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev_a.elapsed_time(ev_b)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)]))
+    t = torch.tensor([ms_total, t_wall * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms_total, wall_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    cells = X * Y * Z
+    value = cells / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (interior jacobi) ----------------------------------
+    peak, peak_src = measured_peaks()
+    dom_cells = jac.interior_cells if jac.overlap else sum(int(np.prod(d.size())) for d in dd.domains())
+    if world == 1 and len(dd.domains()) > 1:
+        # events sit on the first GPU's stream: attribute that subdomain's cells only
+        dom_cells = dom_cells // len(dd.domains())
+    alg_bytes = 2 * es * dom_cells
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm",
+        "kernel": "jacobi_march_kernel (interior region)" if jac.overlap else "jacobi_march_kernel (whole region)",
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "kernel_ms": kern_ms,
+        "traffic": None,
+        "step_frac_of_roofline": (2 * es * cells / ngpu) / (ms_step * 1e-3) / 1e9 / peak,
+    }
+
+    # ---- end to end: host buffers in, host result out, every step ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        d0 = dd.domains()[0]
+        raw = d0.raw_size()
+        nbytes = raw[0] * raw[1] * raw[2] * es
+        pin_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        pin_out = torch.empty(8, dtype=torch.uint8, pin_memory=True)
+        host_field = pin_in.numpy().view(dtype).reshape(raw[::-1])
+        host_field[...] = 0.5
+        res_dev = torch.zeros(1, dtype=torch.float64, device=f"cuda:{d0.gpu()}")
+        lo, hi = d0.get_compute_region()
+        steps_e = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            # host field -> curr (pinned H2D on the compute stream), one iteration, residual -> host
+            sb._lib.check(L.sb_memcpy(d0.curr_[0], pin_in.data_ptr(), nbytes, d0.gpu(), sb._lib.stream_ptr(cs0)))
+            cs0.synchronize()
+            jac.step()
+            sb._lib.check(
+                L.sb_sqdiff(d0.curr_data(0), d0.next_data(0), es, sb._lib.i3(d0.accessor_origin()), sb._lib.i3(lo), sb._lib.i3(hi), res_dev.data_ptr(), sb._lib.stream_ptr(cs0))
+            )
+            sb._lib.check(L.sb_memcpy(pin_out.data_ptr(), res_dev.data_ptr(), 8, d0.gpu(), sb._lib.stream_ptr(cs0)))
+            cs0.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps_e):
+            e2e_step()
+        barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / steps_e], dtype=torch.float64, device="cuda")
+        if world > 1:
+            td.all_reduce(te, op=td.ReduceOp.MAX)
+        e2e = {
+            "value": cells / float(te[0]),
+            "unit": UNIT,
+            "h2d_bytes_per_step": int(nbytes) * max(1, len(dd.domains())) * world,
+            "d2h_bytes_per_step": 8 * world,
+            "ms_per_step": float(te[0]) * 1e3,
+            "steps": steps_e,
+            "definition": "every step: pinned-host field -> curr (H2D), one jacobi iteration through DistributedDomain, L2 residual -> host (D2H)",
+        }
+
+    # ---- CPU baseline (rank 0, N=1, bounded sample) -----------------------------------------
+    cpu = None
+    if rank == 0 and ngpu == 1 and not args.no_cpu_baseline:
+        r = time_cpu(n, dtype, steps=50, warmup=1, budget_s=12.0)
+        cpu = {
+            "value": r["value"],
+            "unit": UNIT,
+            "cores": r["cores"],
+            "kind": "port",
+            "sample": f"{r['steps']} full iterations of {n}^3 {args.dtype} (<=12 s), oracle/stencil_oracle.c with OpenMP on {cpu_model()}",
+        }
+
+    if rank == 0:
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": ngpu,
+            "steps": args.steps,
+            "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": args.dtype,
+            "data": "synthetic",
+            "per_gpu": value / ngpu,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "config": {
+                "workload": f"jacobi3d {n}^3 per GPU radius-1 {args.dtype.upper()} (BASELINE configs[1]); global {X}x{Y}x{Z}",
+                "parallelism": f"{world} process(es) x {len(gpus)} GPU(s), 3-D domain decomposition, fused P2P halo write",
+                "overlap": jac.overlap,
+                "l2": "inputs larger than L2 (2 x %.2f GiB per GPU vs 126 MB)" % (2 * es * (n + 2) ** 3 / 2**31),
+                "init": "0.5 everywhere, hot/cold spheres (bin/jacobi3d.cu:18-63)",
+            },
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    dd.close()
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as td
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        td.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+    try:
+        run_ours(args, rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as td
+
+            td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,161 @@
+/* stencil_b200.h -- C ABI of the B200-native halo-exchange / jacobi hot path.
+ *
+ * This is the drop-in boundary below the C++ API (include/stencil/*.hpp): plain pointers and
+ * sizes, no C++ or torch types.  Each entry point names the interface of cwpearson/stencil it
+ * replaces (paths relative to the reference checkout).  Device pointers are raw CUDA device
+ * addresses (cudaMalloc, cudaIpcOpenMemHandle or peer-mapped); `stream` is a cudaStream_t passed
+ * as void*.  All functions return 0 on success or a negative sb_status; sb_last_error() gives the
+ * message.  Nothing here falls back to the CPU: without a CUDA device every launch fails loudly.
+ *
+ * Memory layout (reference src/local_domain.cu:187-203): quantity allocation = x fastest,
+ * element (x,y,z) at byte offset (z*ysize + y)*pitch + x*elem_size, where (pitch, ysize) are the
+ * cudaPitchedPtr fields the reference carries (pitch == xsize == row bytes, unpitched).
+ */
+#ifndef STENCIL_B200_H
+#define STENCIL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_VERSION 1
+
+typedef enum sb_status {
+  SB_OK = 0,
+  SB_ERR_INVALID = -1, /* bad argument */
+  SB_ERR_CUDA = -2,    /* a CUDA runtime call failed */
+  SB_ERR_NOGPU = -3,   /* no usable CUDA device */
+  SB_ERR_ALLOC = -4
+} sb_status;
+
+/* Thread-local message for the last failing call on this thread. */
+const char *sb_last_error(void);
+int sb_version(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t sb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Geometry.  radius27 is the reference's DirectionMap<size_t> storage order:
+ * radius27[(dz+1)*9 + (dy+1)*3 + (dx+1)]  (include/stencil/direction_map.hpp:15,44-50).
+ * ------------------------------------------------------------------------------------------- */
+
+/* LocalDomain::halo_pos, src/local_domain.cu:86-125 */
+int sb_halo_pos(const int64_t dir[3], const int64_t size[3], const int64_t radius27[27], int halo, int64_t out[3]);
+/* LocalDomain::halo_extent, include/stencil/local_domain.cuh:212-222 */
+int sb_halo_extent(const int64_t dir[3], const int64_t size[3], const int64_t radius27[27], int64_t out[3]);
+/* LocalDomain::raw_size, local_domain.cuh:236-239 */
+int sb_raw_size(const int64_t size[3], const int64_t radius27[27], int64_t out[3]);
+/* prime_factors (descending), src/numeric.cpp:6-26.  Returns the count (<= cap) or <0. */
+int sb_prime_factors(int64_t n, int64_t *out, int cap);
+/* RankPartition, include/stencil/partition.hpp:20-116: dim, base subdomain size, remainder */
+int sb_rank_partition(const int64_t size[3], int64_t n, int64_t dim[3], int64_t base[3], int64_t rem[3]);
+/* NodePartition, partition.hpp:120-256 */
+int sb_node_partition(const int64_t size[3], const int64_t radius27[27], int64_t nodes, int64_t gpus, int64_t sys_dim[3],
+                      int64_t node_dim[3], int64_t base[3], int64_t rem[3]);
+/* subdomain_size / subdomain_origin of either partition, partition.hpp:55-86 */
+int sb_subdomain_size(const int64_t base[3], const int64_t rem[3], const int64_t idx[3], int64_t out[3]);
+int sb_subdomain_origin(const int64_t base[3], const int64_t rem[3], const int64_t idx[3], int64_t out[3]);
+/* DistributedDomain::get_interior / get_exterior for one subdomain, src/stencil.cu:878-977.
+ * lo/hi = compute region of the subdomain (global coords).  Exterior: up to 6 boxes in the order
+ * +x,+y,+z,-x,-y,-z; returns the number written to ext_lo/ext_hi (each 6*3 int64). */
+int sb_interior(const int64_t lo[3], const int64_t hi[3], const int64_t radius27[27], int64_t int_lo[3], int64_t int_hi[3]);
+int sb_exterior(const int64_t lo[3], const int64_t hi[3], const int64_t radius27[27], int64_t *ext_lo, int64_t *ext_hi);
+
+/* ---------------------------------------------------------------------------------------------
+ * Box copies: the one engine behind pack, unpack, translate and the fused direct halo write.
+ * ------------------------------------------------------------------------------------------- */
+
+/* A 3-D strided allocation, the cudaPitchedPtr the reference passes around. */
+typedef struct sb_pitched {
+  void *ptr;
+  int64_t pitch; /* bytes between rows */
+  int64_t ysize; /* rows per z-plane */
+} sb_pitched;
+
+/* One strided->strided copy of `extent` elements (x,y,z) from src@src_pos to dst@dst_pos.
+ * Replaces translate() (src/copy.cu:34-77); with a dense dst it is pack_kernel
+ * (src/pack_kernel.cu:3-59), with a dense src unpack_kernel (:61-108). */
+typedef struct sb_box_copy {
+  sb_pitched dst;
+  int64_t dst_pos[3];
+  sb_pitched src;
+  int64_t src_pos[3];
+  int64_t extent[3];
+  int64_t elem_size;
+} sb_box_copy;
+
+/* pack_kernel / unpack_kernel / translate one-shots (tests launch these directly in the reference:
+ * test/test_cuda_pack.cu:76, test/test_cuda_translate_kernel.cu). */
+int sb_pack(void *dst, sb_pitched src, const int64_t pos[3], const int64_t extent[3], int64_t elem_size, void *stream);
+int sb_unpack(sb_pitched dst, const void *src, const int64_t pos[3], const int64_t extent[3], int64_t elem_size,
+              void *stream);
+int sb_translate(sb_pitched dst, const int64_t dst_pos[3], sb_pitched src, const int64_t src_pos[3],
+                 const int64_t extent[3], int64_t elem_size, void *stream);
+
+/* A persistent plan: any number of box copies executed by ONE kernel launch on `device`.
+ * This is what replaces, per source GPU, the reference's per-message launches of
+ * dev_packer_pack_domain (src/packer.cu:10-26, 109-148), multi_translate (src/copy.cu:79-85,
+ * tx_cuda.cuh:74-104), cudaMemcpyPeerAsync (tx_cuda.cuh:162) and dev_unpacker_unpack_domain
+ * (src/packer.cu:28-44): destination pointers may be local, or a peer GPU's ghost cells
+ * (peer-access or CUDA-IPC mapped), in which case the halo is written straight over NVLink. */
+typedef struct sb_copy_plan sb_copy_plan;
+int sb_copy_plan_create(sb_copy_plan **out, int device, const sb_box_copy *copies, int64_t n);
+int sb_copy_plan_launch(sb_copy_plan *plan, void *stream);
+int64_t sb_copy_plan_bytes(const sb_copy_plan *plan);     /* payload bytes per launch */
+int64_t sb_copy_plan_num_tiles(const sb_copy_plan *plan); /* work items per launch */
+int sb_copy_plan_destroy(sb_copy_plan *plan);
+
+/* Cross-GPU completion flags for the fused exchange when source and destination GPUs are driven
+ * by different processes (the reference's IPC event + 0-byte MPI notify, tx_cuda.cuh:225-315,
+ * src/tx_ipc.cpp).  flags are uint32 slots in device memory that peers map via CUDA IPC.
+ *  - sb_signal: after all prior work on `stream`, store `value` (release, system scope) to each
+ *    of the n remote slots.
+ *  - sb_wait:   make `stream` wait until each of n local slots is >= value (acquire). */
+int sb_signal(uint32_t *const *remote_slots, int n, uint32_t value, int device, void *stream);
+int sb_wait(const uint32_t *local_slots, int n, uint32_t value, int device, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 7-point jacobi step (the reference's user kernel, bin/jacobi3d.cu:40-85) over a region.
+ * dtype_size 4 = float, 8 = double.  acc_origin = global coordinate of allocation element (0,0,0)
+ * (Accessor origin, include/stencil/local_domain.cuh:153-173).  [lo,hi) = region to update,
+ * [clo,chi) = the whole distributed compute region (hot/cold sphere placement).
+ * dst[p] = 1 in the hot sphere, 0 in the cold sphere, else ((((((0+px)+mx)+py)+my)+pz)+mz)/6 with
+ * IEEE round-to-nearest division (bit-identical to the CPU oracle).
+ * ------------------------------------------------------------------------------------------- */
+int sb_jacobi3d(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3],
+                const int64_t hi[3], const int64_t clo[3], const int64_t chi[3], void *stream);
+/* init_kernel, bin/jacobi3d.cu:18-29: fill region with a constant */
+int sb_fill(sb_pitched dst, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3], const int64_t hi[3],
+            double value, void *stream);
+/* sum over [lo,hi) of (a-b)^2 accumulated in double into *out_dev (device double, zeroed by the
+ * call): the FP64 residual BASELINE.json asks for (not in the reference). */
+int sb_sqdiff(sb_pitched a, sb_pitched b, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3],
+              const int64_t hi[3], double *out_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device memory + peer plumbing used by the host layers (C++ and Python).
+ * ------------------------------------------------------------------------------------------- */
+int sb_device_count(int *count);
+int sb_malloc(void **ptr, size_t bytes, int device);
+int sb_free(void *ptr, int device);
+int sb_memset(void *ptr, int value, size_t bytes, int device, void *stream);
+/* cudaMemcpyAsync(cudaMemcpyDefault) on `stream` of `device`: host<->device and device<->device (UVA).
+ * Host buffers should be pinned for the copy to be asynchronous. */
+int sb_memcpy(void *dst, const void *src, size_t bytes, int device, void *stream);
+int sb_stream_sync(int device, void *stream);
+int sb_device_sync(int device);
+/* cudaDeviceEnablePeerAccess both ways if possible (gpu_topo::enable_peer, src/gpu_topology.cpp:97-129);
+ * *ok = 1 when src can address dst's memory. */
+int sb_enable_peer(int src_device, int dst_device, int *ok);
+/* CUDA IPC handle export / import (cudaIpcGetMemHandle / OpenMemHandle, tx_cuda.cuh:225-243). handle = 64 bytes. */
+int sb_ipc_export(void *ptr, void *handle64);
+int sb_ipc_import(const void *handle64, int device, void **ptr);
+int sb_ipc_close(void *ptr, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STENCIL_B200_H */

@@ -1,0 +1,360 @@
+// 7-point jacobi kernels for sm_100a (see jacobi.cuh).
+//
+// jacobi_march_kernel: register-blocked z-march.  A warp owns a strip of 32*VX cells in x and RY
+// rows in y; each lane keeps the z-1 / z / z+1 values of its VX*RY columns in registers, so every
+// cell of the subdomain is fetched from HBM exactly once (as the z+1 "centre" of its own column)
+// with 16-byte vector loads.  x-neighbours come from the adjacent lane by warp shuffle (lanes 0
+// and 31 fetch one scalar), y-neighbours inside the RY rows from registers and across warps from
+// L1 (the neighbouring warp loaded that row one step earlier).  Eight warps are stacked in y, the
+// z axis is cut into chunks so that the grid has several waves on 148 SMs, and an optional
+// prefetch.global.L2 runs a few planes ahead of the march to deepen the memory pipeline without
+// spending registers.  Algorithmic traffic: one read + one write per cell (2*sizeof(T) B/cell).
+//
+// Numerics: sum order ((((((0+px)+mx)+py)+my)+pz)+mz) as in bin/jacobi3d.cu:66-77, then an exact
+// IEEE division by 6 done as q = v*c; r = fma(-6,q,v); q' = fma(r,c,q) with c = RN(1/6)
+// (Markstein's correction: q' is the correctly rounded quotient), so results are bit-identical
+// to the CPU oracle's `v / 6` in both FP32 and FP64.
+#include "jacobi.cuh"
+
+namespace sb {
+namespace {
+
+template <typename T> struct Num;
+template <> struct Num<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float div6(float v) {
+    const float c = 1.0f / 6.0f;
+    const float q = __fmul_rn(v, c);
+    const float r = __fmaf_rn(-6.0f, q, v);
+    return __fmaf_rn(r, c, q);
+  }
+};
+template <> struct Num<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double div6(double v) {
+    const double c = 1.0 / 6.0;
+    const double q = __dmul_rn(v, c);
+    const double r = __fma_rn(-6.0, q, v);
+    return __fma_rn(r, c, q);
+  }
+};
+
+template <typename T, int N> struct alignas(sizeof(T) * N) Vec { T v[N]; };
+
+// dist() of bin/jacobi3d.cu:31-33: int64(__fsqrt_rn(float(d2)))
+__device__ __forceinline__ bool in_sphere(int d2, int rad) { return (int)__fsqrt_rn((float)d2) <= rad; }
+
+template <typename T> __device__ __forceinline__ T stencil_value(T px, T mx, T py, T my, T pz, T mz) {
+  T v = Num<T>::add(T(0), px);
+  v = Num<T>::add(v, mx);
+  v = Num<T>::add(v, py);
+  v = Num<T>::add(v, my);
+  v = Num<T>::add(v, pz);
+  v = Num<T>::add(v, mz);
+  return Num<T>::div6(v);
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+template <typename T, int VX, int RY>
+__global__ void __launch_bounds__(256) jacobi_march_kernel(const __grid_constant__ JacobiParams p, int tiles_x, int tiles_y) {
+  using V = Vec<T, VX>;
+  constexpr int WY = 8; // warps stacked in y
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+
+  int b = blockIdx.x;
+  const int bx = b % tiles_x;
+  b /= tiles_x;
+  const int by = b % tiles_y;
+  const int bz = b / tiles_y;
+
+  const int x = (p.lo[0] / VX) * VX + (bx * 32 + lane) * VX; // first cell of this lane (allocation index)
+  const int y = p.lo[1] + (by * WY + warp) * RY;             // first row of this warp
+  const int z0 = p.lo[2] + bz * p.zchunk;
+  const int z1 = min(z0 + p.zchunk, p.hi[2]);
+  if (y >= p.hi[1]) return;                                                  // warp-uniform
+  if ((p.lo[0] / VX) * VX + bx * 32 * VX >= p.hi[0]) return;                 // warp-uniform
+
+  const bool xin = (x + VX <= p.raw[0]); // vector lies inside the allocation row
+  const long long xoff = (long long)x * (long long)sizeof(T);
+
+  auto row = [&](int yy, int zz) -> const char * {
+    yy = clampi(yy, 0, p.raw[1] - 1);
+    zz = clampi(zz, 0, p.raw[2] - 1);
+    return p.src + (long long)zz * p.slice + (long long)yy * p.pitch;
+  };
+  auto ldv = [&](const char *r) -> V {
+    V out;
+    if (xin) {
+      out = *reinterpret_cast<const V *>(r + xoff);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VX; ++i) out.v[i] = T(0);
+    }
+    return out;
+  };
+
+  V prev[RY], cur[RY], nxt[RY];
+#pragma unroll
+  for (int j = 0; j < RY; ++j) {
+    prev[j] = ldv(row(y + j, z0 - 1));
+    cur[j] = ldv(row(y + j, z0));
+  }
+
+  // which scalar this lane fetches for the strip ends (lane 0: x-1, lane 31: x+VX)
+  const bool edge_lane = (lane == 0) || (lane == 31);
+  const int hx = clampi(lane == 0 ? x - 1 : x + VX, 0, p.raw[0] - 1);
+  const long long hoff = (long long)hx * (long long)sizeof(T);
+
+  const int rr = (p.rad + 1) * (p.rad + 1);
+
+  for (int z = z0; z < z1; ++z) {
+#pragma unroll
+    for (int j = 0; j < RY; ++j) nxt[j] = ldv(row(y + j, z + 1));
+    if (p.prefetch > 0 && xin) {
+      const int zp = z + 1 + p.prefetch;
+      if (zp < p.raw[2]) {
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          const char *a = row(y + j, zp) + xoff;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+      }
+    }
+    const V up = ldv(row(y - 1, z));
+    const V dn = ldv(row(y + RY, z));
+
+    const int gz = z + p.org[2];
+    const int dz2 = (gz - p.cz) * (gz - p.cz);
+
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      T h = T(0);
+      if (edge_lane) h = *reinterpret_cast<const T *>(row(y + j, z) + hoff);
+      T left = __shfl_up_sync(0xffffffffu, cur[j].v[VX - 1], 1);
+      T right = __shfl_down_sync(0xffffffffu, cur[j].v[0], 1);
+      if (lane == 0) left = h;
+      if (lane == 31) right = h;
+
+      const int gy = y + j + p.org[1];
+      const int dyz2 = (gy - p.cy) * (gy - p.cy) + dz2;
+      const bool near_sphere = dyz2 < rr; // exact row pre-filter, see oracle/stencil_oracle.c
+
+      V out;
+#pragma unroll
+      for (int i = 0; i < VX; ++i) {
+        const T px = (i < VX - 1) ? cur[j].v[i + 1 < VX ? i + 1 : i] : right;
+        const T mx = (i > 0) ? cur[j].v[i > 0 ? i - 1 : 0] : left;
+        const T py = (j < RY - 1) ? cur[j + 1 < RY ? j + 1 : j].v[i] : dn.v[i];
+        const T my = (j > 0) ? cur[j > 0 ? j - 1 : 0].v[i] : up.v[i];
+        T val = stencil_value<T>(px, mx, py, my, nxt[j].v[i], prev[j].v[i]);
+        if (near_sphere) {
+          const int gx = x + i + p.org[0];
+          const int dh = (gx - p.hot_x) * (gx - p.hot_x) + dyz2;
+          const int dc = (gx - p.cold_x) * (gx - p.cold_x) + dyz2;
+          if (in_sphere(dh, p.rad)) {
+            val = T(1);
+          } else if (in_sphere(dc, p.rad)) {
+            val = T(0);
+          }
+        }
+        out.v[i] = val;
+      }
+
+      if (y + j < p.hi[1]) {
+        char *drow = p.dst + (long long)z * p.slice + (long long)(y + j) * p.pitch;
+        if (x >= p.lo[0] && x + VX <= p.hi[0]) {
+          *reinterpret_cast<V *>(drow + xoff) = out;
+        } else {
+#pragma unroll
+          for (int i = 0; i < VX; ++i) {
+            if (x + i >= p.lo[0] && x + i < p.hi[0]) reinterpret_cast<T *>(drow)[x + i] = out.v[i];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      prev[j] = cur[j];
+      cur[j] = nxt[j];
+    }
+  }
+}
+
+// One thread per cell: thin regions (the +-x exterior slabs are 1..r cells wide in x).
+// Threads run fastest along y there so a warp's accesses land in 32 different rows but the
+// same few sectors per row; z-neighbours of consecutive planes hit L2.
+template <typename T> __global__ void __launch_bounds__(256) jacobi_cell_kernel(const __grid_constant__ JacobiParams p) {
+  const int ex = p.hi[0] - p.lo[0], ey = p.hi[1] - p.lo[1], ez = p.hi[2] - p.lo[2];
+  const long long total = (long long)ex * ey * ez;
+  const int rr = (p.rad + 1) * (p.rad + 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // y fastest, then x, then z
+    const int yy = (int)(i % ey);
+    const long long t = i / ey;
+    const int xx = (int)(t % ex);
+    const int zz = (int)(t / ex);
+    const int x = p.lo[0] + xx, y = p.lo[1] + yy, z = p.lo[2] + zz;
+    const char *c = p.src + (long long)z * p.slice + (long long)y * p.pitch + (long long)x * (long long)sizeof(T);
+    const T px = *reinterpret_cast<const T *>(c + sizeof(T));
+    const T mx = *reinterpret_cast<const T *>(c - sizeof(T));
+    const T py = *reinterpret_cast<const T *>(c + p.pitch);
+    const T my = *reinterpret_cast<const T *>(c - p.pitch);
+    const T pz = *reinterpret_cast<const T *>(c + p.slice);
+    const T mz = *reinterpret_cast<const T *>(c - p.slice);
+    T val = stencil_value<T>(px, mx, py, my, pz, mz);
+    const int gx = x + p.org[0], gy = y + p.org[1], gz = z + p.org[2];
+    const int dyz2 = (gy - p.cy) * (gy - p.cy) + (gz - p.cz) * (gz - p.cz);
+    if (dyz2 < rr) {
+      const int dh = (gx - p.hot_x) * (gx - p.hot_x) + dyz2;
+      const int dc = (gx - p.cold_x) * (gx - p.cold_x) + dyz2;
+      if (in_sphere(dh, p.rad)) {
+        val = T(1);
+      } else if (in_sphere(dc, p.rad)) {
+        val = T(0);
+      }
+    }
+    *reinterpret_cast<T *>(p.dst + (long long)z * p.slice + (long long)y * p.pitch + (long long)x * (long long)sizeof(T)) = val;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fill_kernel(char *dst, long long pitch, long long slice, int lx, int ly, int lz, int ex,
+                                                   int ey, int ez, T value) {
+  const long long total = (long long)ex * ey * ez;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % ex);
+    const long long t = i / ex;
+    const int yy = (int)(t % ey);
+    const int zz = (int)(t / ey);
+    reinterpret_cast<T *>(dst + (long long)(lz + zz) * slice + (long long)(ly + yy) * pitch)[lx + xx] = value;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sqdiff_kernel(const char *a, const char *b, long long pitch, long long slice, int lx,
+                                                     int ly, int lz, int ex, int ey, int ez, double *out) {
+  const long long total = (long long)ex * ey * ez;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % ex);
+    const long long t = i / ex;
+    const int yy = (int)(t % ey);
+    const int zz = (int)(t / ey);
+    const long long off = (long long)(lz + zz) * slice + (long long)(ly + yy) * pitch;
+    const double d = (double)reinterpret_cast<const T *>(a + off)[lx + xx] - (double)reinterpret_cast<const T *>(b + off)[lx + xx];
+    acc += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double wsum[8];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += wsum[w];
+    atomicAdd(out, s);
+  }
+}
+
+template <typename T, int VX> int launch_march(const JacobiParams &p, int ry, cudaStream_t stream) {
+  const int x0a = (p.lo[0] / VX) * VX;
+  const int tiles_x = (p.hi[0] - x0a + 32 * VX - 1) / (32 * VX);
+  const int ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
+  const int tiles_z = (nz + p.zchunk - 1) / p.zchunk;
+  auto go = [&](auto kern, int RY) {
+    const int tiles_y = (ny + 8 * RY - 1) / (8 * RY);
+    const long long blocks = (long long)tiles_x * tiles_y * tiles_z;
+    kern<<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
+  };
+  switch (ry) {
+  case 1:
+    go(jacobi_march_kernel<T, VX, 1>, 1);
+    break;
+  case 4:
+    go(jacobi_march_kernel<T, VX, 4>, 4);
+    break;
+  default:
+    go(jacobi_march_kernel<T, VX, 2>, 2);
+    break;
+  }
+  return 1;
+}
+
+int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+} // namespace
+
+int launch_jacobi(const JacobiParams &p_in, int dtype_size, cudaStream_t stream) {
+  JacobiParams p = p_in;
+  const int ex = p.hi[0] - p.lo[0], ey = p.hi[1] - p.lo[1], ez = p.hi[2] - p.lo[2];
+  if (ex <= 0 || ey <= 0 || ez <= 0) return 0;
+
+  static const int ry = env_int("SB_JACOBI_RY", 2);
+  static const int zchunk_env = env_int("SB_JACOBI_ZCHUNK", 0);
+  static const int pf = env_int("SB_JACOBI_PREFETCH", 4);
+  static const int thin = env_int("SB_JACOBI_THIN_X", 16);
+
+  if (ex < thin) {
+    const long long total = (long long)ex * ey * ez;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (dtype_size == 4)
+      jacobi_cell_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    else
+      jacobi_cell_kernel<double><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    return 1;
+  }
+
+  // z chunk: enough CTAs for >= ~6 waves of 148 SMs x 4 resident CTAs, but chunks no shorter than 16 planes
+  if (zchunk_env > 0) {
+    p.zchunk = zchunk_env;
+  } else if (p.zchunk <= 0) {
+    p.zchunk = 64;
+  }
+  if (p.zchunk > ez) p.zchunk = ez;
+  p.prefetch = pf;
+
+  const unsigned long long a = (unsigned long long)(uintptr_t)p.src | (unsigned long long)(uintptr_t)p.dst |
+                               (unsigned long long)p.pitch | (unsigned long long)p.slice;
+  if (dtype_size == 8) {
+    if (a % 16 == 0) return launch_march<double, 2>(p, ry, stream);
+    return launch_march<double, 1>(p, ry, stream);
+  }
+  if (a % 16 == 0) return launch_march<float, 4>(p, ry, stream);
+  if (a % 8 == 0) return launch_march<float, 2>(p, ry, stream);
+  return launch_march<float, 1>(p, ry, stream);
+}
+
+int launch_fill(char *dst, long long pitch, long long slice, const int lo[3], const int hi[3], int dtype_size, double value,
+                cudaStream_t stream) {
+  const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+  if (ex <= 0 || ey <= 0 || ez <= 0) return 0;
+  long long blocks = ((long long)ex * ey * ez + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype_size == 4)
+    fill_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(dst, pitch, slice, lo[0], lo[1], lo[2], ex, ey, ez, (float)value);
+  else
+    fill_kernel<double><<<(unsigned)blocks, 256, 0, stream>>>(dst, pitch, slice, lo[0], lo[1], lo[2], ex, ey, ez, value);
+  return 1;
+}
+
+int launch_sqdiff(const char *a, const char *b, long long pitch, long long slice, const int lo[3], const int hi[3],
+                  int dtype_size, double *out_dev, cudaStream_t stream) {
+  cudaMemsetAsync(out_dev, 0, sizeof(double), stream);
+  const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+  if (ex <= 0 || ey <= 0 || ez <= 0) return 0;
+  long long blocks = ((long long)ex * ey * ez + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (dtype_size == 4)
+    sqdiff_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(a, b, pitch, slice, lo[0], lo[1], lo[2], ex, ey, ez, out_dev);
+  else
+    sqdiff_kernel<double><<<(unsigned)blocks, 256, 0, stream>>>(a, b, pitch, slice, lo[0], lo[1], lo[2], ex, ey, ez, out_dev);
+  return 1;
+}
+
+} // namespace sb

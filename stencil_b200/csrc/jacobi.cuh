@@ -1,0 +1,34 @@
+// 7-point jacobi step with hot/cold Dirichlet spheres -- B200 rewrite of the reference's user
+// kernel (bin/jacobi3d.cu:40-85).  Bandwidth-bound pointwise stencil: no tensor cores.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sb {
+
+struct JacobiParams {
+  char *dst;       // allocation base (element 0,0,0)
+  const char *src; // allocation base
+  long long pitch; // bytes between rows (same for src and dst)
+  long long slice; // bytes between planes
+  int raw[3];      // allocation size in elements (x,y,z)
+  int lo[3];       // region to update, ALLOCATION-relative element coordinates
+  int hi[3];
+  int org[3];    // global coordinate of allocation element (0,0,0)
+  int hot_x;     // sphere centres (global coordinates), shared y/z
+  int cold_x;
+  int cy, cz;
+  int rad;       // sphere radius
+  int zchunk;    // planes marched per CTA
+  int prefetch;  // L2 prefetch distance in planes (0 = off)
+};
+
+// returns the number of kernel launches issued (0 if the region is empty)
+int launch_jacobi(const JacobiParams &p, int dtype_size, cudaStream_t stream);
+int launch_fill(char *dst, long long pitch, long long slice, const int lo[3], const int hi[3], int dtype_size, double value,
+                cudaStream_t stream);
+int launch_sqdiff(const char *a, const char *b, long long pitch, long long slice, const int lo[3], const int hi[3],
+                  int dtype_size, double *out_dev, cudaStream_t stream);
+
+} // namespace sb

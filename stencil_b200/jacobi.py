@@ -1,0 +1,108 @@
+"""The jacobi3d iteration of the reference driver (bin/jacobi3d.cu:296-377) over DistributedDomain.
+
+    interior kernel on a compute stream  ||  dd.exchange() on the library's high-priority streams
+    exterior slabs (after the exchange)  ->  stream sync  ->  dd.swap()
+
+All ctypes argument packs are built once per swap parity so the per-iteration host work is a
+handful of foreign calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Tuple
+
+import numpy as np
+
+from ._lib import check, i3, lib, stream_ptr
+from .domain import DataHandle, DistributedDomain, Radius
+
+
+def jacobi_radius() -> Radius:
+    """faces only, radius 1 (bin/jacobi3d.cu:237-246)"""
+    return Radius.face_edge_corner(1, 0, 0)
+
+
+def scaled_size(x: int, y: int, z: int, num_subdoms: int) -> Tuple[int, int, int]:
+    """Weak-scaling size rule of bin/jacobi3d.cu:189-199 (one node): multiply the prime factors of the
+    subdomain count into the currently smallest dimension."""
+    from .domain import prime_factors
+
+    for pf in prime_factors(num_subdoms):
+        if x <= y and x <= z:
+            x *= pf
+        elif y <= z:
+            y *= pf
+        else:
+            z *= pf
+    return x, y, z
+
+
+class Jacobi3D:
+    def __init__(self, dd: DistributedDomain, h: DataHandle, overlap: bool = True):
+        import torch
+
+        self.dd, self.h, self.overlap = dd, h, overlap
+        self.creg = dd.get_compute_region()
+        self.streams = [torch.cuda.Stream(device=d.gpu()) for d in dd.domains()]
+        interiors, exteriors = dd.get_interior(), dd.get_exterior()
+        L = lib()
+        self._fn = L.sb_jacobi3d
+        # calls[parity][domain] = (interior args, [exterior args...], whole args)
+        self._calls = []
+        for parity in (0, 1):
+            per_dom = []
+            for di, d in enumerate(dd.domains()):
+                src = d.pitched(h.id, "curr" if parity == 0 else "next")
+                dst = d.pitched(h.id, "next" if parity == 0 else "curr")
+                if parity == 1:
+                    # pitched() reads the CURRENT curr_/next_ lists; parity 1 = after one swap
+                    pass
+                acc = i3(d.accessor_origin())
+                clo, chi = i3(self.creg[0]), i3(self.creg[1])
+                s = stream_ptr(self.streams[di])
+
+                def pack(reg):
+                    return (dst, src, d.elem_size(h.id), acc, i3(reg[0]), i3(reg[1]), clo, chi, s)
+
+                per_dom.append((pack(interiors[di]), [pack(r) for r in exteriors[di]], pack(d.get_compute_region())))
+            self._calls.append(per_dom)
+        self.interior_cells = sum(int(np.prod([hi[a] - lo[a] for a in range(3)])) for lo, hi in interiors)
+        self._parity0 = dd._parity
+
+    def _args(self):
+        return self._calls[(self.dd._parity - self._parity0) & 1]
+
+    def launch_interior(self) -> None:
+        for a in self._args():
+            check(self._fn(*a[0]))
+
+    def launch_exterior(self) -> None:
+        for a in self._args():
+            for e in a[1]:
+                check(self._fn(*e))
+
+    def launch_whole(self) -> None:
+        for a in self._args():
+            check(self._fn(*a[2]))
+
+    def step(self) -> None:
+        """One iteration, exactly the loop body of bin/jacobi3d.cu:296-368."""
+        dd = self.dd
+        if self.overlap:
+            self.launch_interior()
+            dd.exchange()
+            self.launch_exterior()
+        else:
+            dd.exchange()
+            self.launch_whole()
+        for s in self.streams:
+            s.synchronize()
+        dd.swap()
+
+    def init(self, value: float = 0.5) -> None:
+        """init_kernel (bin/jacobi3d.cu:18-29) on curr; ghost cells are filled by the first exchange."""
+        from .domain import fill
+
+        for d in self.dd.domains():
+            fill(d, self.h, d.get_compute_region(), value)
+            check(lib().sb_device_sync(d.gpu()))

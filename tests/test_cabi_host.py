@@ -1,0 +1,122 @@
+"""CPU-side checks of the product's C ABI: the library loads, exports every symbol the header declares,
+and its host-side geometry / partition logic agrees with the reference-generated golden vectors and the
+oracle.  No GPU compute is invoked here."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import stencil_b200 as sb
+from oracle import geometry as g
+from stencil_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_geometry.json")))
+
+
+def radius27(tab):
+    r = sb.Radius()
+    i = 0
+    for z in (-1, 0, 1):
+        for y in (-1, 0, 1):
+            for x in (-1, 0, 1):
+                r.set_dir((x, y, z), tab[i])
+                i += 1
+    return r
+
+
+RADII = {k: radius27(v) for k, v in GOLD["radii"].items()}
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "stencil_b200.h")).read()
+    declared = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"sb_status"}
+    assert len(declared) >= 30
+    L = C.CDLL(sb.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    # and the ctypes table covers exactly the header
+    assert declared == set(_lib._SIGS), declared ^ set(_lib._SIGS)
+    assert sb.lib().sb_version() == 1
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libstencil_b200.so")
+    with pytest.raises(sb.StencilError):
+        _lib.lib()
+
+
+def test_radius_constructors():
+    assert list(sb.Radius.constant(3).c27()) == GOLD["radii"]["c3"]
+    assert list(sb.Radius.face_edge_corner(2, 1, 0).c27()) == GOLD["radii"]["f2e1"]
+    assert list(sb.Radius.face_edge_corner(3, 2, 1).c27()) == GOLD["radii"]["f3e2c1"]
+    r = sb.Radius.constant(0)
+    r.set_face(1)
+    assert r == sb.Radius.face_edge_corner(1, 0, 0)
+
+
+def test_halo_geometry_vs_reference():
+    for c in GOLD["halo"]:
+        sz, r = tuple(c["size"]), RADII[c["radius"]]
+        for d in c["dirs"]:
+            dv = tuple(d["dir"])
+            assert list(sb.halo_pos(dv, sz, r, True)) == d["pos_halo"]
+            assert list(sb.halo_pos(dv, sz, r, False)) == d["pos_interior"]
+            assert list(sb.halo_extent(dv, sz, r)) == d["extent"]
+    for c in GOLD["local_domain"]:
+        assert list(sb.raw_size(tuple(c["size"]), RADII[c["radius"]])) == c["raw_size"]
+
+
+def test_bad_direction_is_an_error():
+    with pytest.raises(sb.StencilError):
+        sb.halo_pos((2, 0, 0), (4, 4, 4), sb.Radius.constant(1), True)
+
+
+def test_prime_factors_vs_reference():
+    for n, f in GOLD["prime_factors"].items():
+        assert sb.prime_factors(int(n)) == f
+
+
+def test_partitions_vs_reference():
+    for c in GOLD["node_partition"]:
+        p = sb.Partition(tuple(c["size"]), RADII[c["radius"]], c["nodes"], c["gpus"])
+        assert list(p.sys_dim) == c["sys_dim"] and list(p.node_dim) == c["node_dim"]
+        for s in c["subdomains"]:
+            assert list(p.subdomain_size(tuple(s["idx"]))) == s["size"]
+            assert list(p.subdomain_origin(tuple(s["idx"]))) == s["origin"]
+    for c in GOLD["rank_partition"]:
+        p = sb.Partition(tuple(c["size"]), sb.Radius.constant(0), 1, c["n"], trivial=True)
+        assert list(p.dim) == c["dim"]
+        for s in c["subdomains"]:
+            assert list(p.subdomain_size(tuple(s["idx"]))) == s["size"]
+            assert list(p.subdomain_origin(tuple(s["idx"]))) == s["origin"]
+
+
+def test_interior_exterior_vs_oracle():
+    L = sb.lib()
+    for name, tab in GOLD["radii"].items():
+        r, ro = RADII[name], g.Radius()
+        i = 0
+        for z in (-1, 0, 1):
+            for y in (-1, 0, 1):
+                for x in (-1, 0, 1):
+                    ro.set_dir((x, y, z), tab[i])
+                    i += 1
+        for lo, hi in [((0, 0, 0), (512, 512, 512)), ((5, 0, 10), (25, 30, 50)), ((0, 0, 0), (3, 3, 3))]:
+            ilo, ihi = _lib.o3(), _lib.o3()
+            _lib.check(L.sb_interior(_lib.i3(lo), _lib.i3(hi), r.c27(), ilo, ihi))
+            assert (_lib.t3(ilo), _lib.t3(ihi)) == g.get_interior(lo, hi, ro)
+            elo, ehi = (C.c_int64 * 18)(), (C.c_int64 * 18)()
+            n = _lib.check(L.sb_exterior(_lib.i3(lo), _lib.i3(hi), r.c27(), elo, ehi))
+            got = [(tuple(elo[3 * k : 3 * k + 3]), tuple(ehi[3 * k : 3 * k + 3])) for k in range(n)]
+            assert got == g.get_exterior(lo, hi, ro)
+
+
+def test_neighbor_wrap_vs_reference():
+    for p, lim, w in GOLD["wrap"]:
+        assert list(sb.get_neighbor(tuple(p), (0, 0, 0), tuple(lim))) == w
