@@ -1,16 +1,34 @@
 # stencil_b200 build: hand-written sm_100a CUDA, no cmake needed.
-#   make            -> stencil_b200/libstencil_b200.so (C ABI + kernels), lib/libstencil.a (C++ API)
+#   make            -> stencil_b200/libstencil_b200.so (C ABI + kernels) and lib/libstencil.a (C++ API, -rdc)
+#   make drivers    -> bin/ : the REFERENCE's own drivers and Catch2 suites compiled, unchanged, from
+#                      $(REF)/bin and $(REF)/test against OUR headers and library (needs $(REF))
 #   make oracle     -> oracle/_build/liboracle.so (test infrastructure)
 NVCC      ?= /usr/local/cuda/bin/nvcc
+REF       ?= /root/reference
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
+NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-comment --expt-relaxed-constexpr
 INC       := -Iinclude -Istencil_b200/csrc
 
+# ---- core: kernels + C ABI (shared library, loaded by python and linked by the C++ API)
 CSRC      := stencil_b200/csrc/box_copy.cu stencil_b200/csrc/jacobi.cu stencil_b200/csrc/capi.cu
 COBJ      := $(patsubst stencil_b200/csrc/%.cu,build/csrc/%.o,$(CSRC))
 SO        := stencil_b200/libstencil_b200.so
 
-all: $(SO)
+# ---- C++ API (static library with relocatable device code, like the reference's stencil::stencil)
+APIDEFS   := -DSTENCIL_USE_MPI=1 -DSTENCIL_USE_CUDA=1 -DSTENCIL_USE_CUDA_AWARE_MPI=1 -DSTENCIL_USE_CUDA_GRAPH=1 \
+             -DSTENCIL_SETUP_STATS=1 -DSTENCIL_OUTPUT_LEVEL=2 -DNDEBUG
+APIINC    := -Iinclude -Iinclude/mpi_shim -I/usr/local/cuda/include/nvtx3
+APIFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -rdc=true --expt-extended-lambda -Xcompiler -fPIC -Xcompiler -Wall \
+             -Xcompiler -Wno-comment -x cu $(APIDEFS) $(APIINC)
+APISRC    := src/compat_kernels.cu src/local_domain.cu src/packer.cu src/translator.cu src/stencil.cu \
+             src/numeric.cpp src/timer.cpp src/rcstream.cpp src/topology.cpp src/gpu_topology.cpp \
+             src/placement_intranoderandom.cpp src/mpi_shim.cpp
+APIOBJ    := $(patsubst src/%,build/api/%.o,$(APISRC))
+# the core objects are compiled a second time with -rdc for the static library
+CAPIOBJ   := $(patsubst stencil_b200/csrc/%.cu,build/api/csrc_%.o,$(CSRC))
+LIBA      := lib/libstencil.a
+
+all: $(SO) $(LIBA)
 
 build/csrc/%.o: stencil_b200/csrc/%.cu $(wildcard stencil_b200/csrc/*.cuh) include/stencil_b200.h $(wildcard include/stencil/*.hpp)
 	@mkdir -p $(dir $@)
@@ -23,10 +41,58 @@ build/numeric.o: src/numeric.cpp include/stencil/numeric.hpp
 $(SO): $(COBJ) build/numeric.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared
 
+build/api/%.o: src/% $(wildcard include/stencil/*) include/stencil_b200.h include/mpi_shim/mpi.h
+	@mkdir -p $(dir $@)
+	$(NVCC) $(APIFLAGS) -c $< -o $@
+
+build/api/csrc_%.o: stencil_b200/csrc/%.cu $(wildcard stencil_b200/csrc/*.cuh) include/stencil_b200.h $(wildcard include/stencil/*.hpp)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(APIFLAGS) -Istencil_b200/csrc -c $< -o $@
+
+$(LIBA): $(APIOBJ) $(CAPIOBJ)
+	@mkdir -p lib
+	rm -f $@ && ar rcs $@ $^
+
+# ---- the reference's unchanged drivers / tests against our library
+DRVFLAGS  := -O3 -std=c++14 $(ARCH) -lineinfo -rdc=true --expt-extended-lambda -Xcompiler -w -w -x cu $(APIDEFS) \
+             -DCATCH_CONFIG_NO_POSIX_SIGNALS $(APIINC) -I$(REF)/thirdparty -I$(REF)/bin
+DRVLINK   := $(ARCH) -rdc=true -L/usr/local/cuda/lib64/stubs -lnvidia-ml -ldl -lcudart
+DRIVERS   := jacobi3d jacobi3d_strong bench_exchange bench_pack exchange_weak exchange_strong
+TESTCUDA  := test_cuda_main test_cuda_align test_cuda_local_domain test_cuda_pack test_cuda_packer test_cuda_rcstream \
+             test_cuda_translate test_cuda_translate_kernel test_cuda_gpu_topo test_exchange
+TESTCPU   := test_cpu_main test_cpu_partition test_cpu_numeric test_cpu_radius test_cpu_accessor test_cpu_tx \
+             test_cpu_mat2d test_cpu_qap
+
+build/drv/%.o: $(REF)/bin/%.cu $(wildcard include/stencil/*)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(DRVFLAGS) -c $< -o $@
+build/drv/statistics.o: $(REF)/bin/statistics.cpp
+	@mkdir -p $(dir $@)
+	$(NVCC) $(DRVFLAGS) -c $< -o $@
+build/drv/t_%.o: $(REF)/test/%.cu $(wildcard include/stencil/*)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(DRVFLAGS) -c $< -o $@
+build/drv/t_%.o: $(REF)/test/%.cpp $(wildcard include/stencil/*)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(DRVFLAGS) -c $< -o $@
+
+bin/%: build/drv/%.o build/drv/statistics.o $(LIBA)
+	@mkdir -p bin
+	$(NVCC) $(DRVLINK) -o $@ $< build/drv/statistics.o $(LIBA)
+bin/test_cuda: $(patsubst %,build/drv/t_%.o,$(TESTCUDA)) $(LIBA)
+	@mkdir -p bin
+	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/t_%.o,$(TESTCUDA)) $(LIBA)
+bin/test_cpu: $(patsubst %,build/drv/t_%.o,$(TESTCPU)) $(LIBA)
+	@mkdir -p bin
+	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/t_%.o,$(TESTCPU)) $(LIBA)
+
+drivers: $(patsubst %,bin/%,$(DRIVERS)) bin/test_cuda bin/test_cpu
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build $(SO) lib
+	rm -rf build $(SO) lib bin
 
-.PHONY: all oracle clean
+.PHONY: all drivers oracle clean
+.SECONDARY:

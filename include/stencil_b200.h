@@ -127,6 +127,10 @@ int sb_wait(const uint32_t *local_slots, int n, uint32_t value, int device, void
  * ------------------------------------------------------------------------------------------- */
 int sb_jacobi3d(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3],
                 const int64_t hi[3], const int64_t clo[3], const int64_t chi[3], void *stream);
+/* The same update over n <= 8 regions in ONE launch: the exterior slabs of a subdomain
+ * (bin/jacobi3d.cu:324-342 launches stencil_kernel once per slab).  lo/hi are n*3 int64. */
+int sb_jacobi3d_regions(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], int n,
+                        const int64_t *lo, const int64_t *hi, const int64_t clo[3], const int64_t chi[3], void *stream);
 /* init_kernel, bin/jacobi3d.cu:18-29: fill region with a constant */
 int sb_fill(sb_pitched dst, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3], const int64_t hi[3],
             double value, void *stream);

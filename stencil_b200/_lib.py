@@ -64,6 +64,7 @@ _SIGS = {
     "sb_signal": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_int, C.c_void_p]),
     "sb_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p]),
     "sb_jacobi3d": (C.c_int, [Pitched, Pitched, C.c_int, I3, I3, I3, I3, I3, C.c_void_p]),
+    "sb_jacobi3d_regions": (C.c_int, [Pitched, Pitched, C.c_int, I3, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), I3, I3, C.c_void_p]),
     "sb_fill": (C.c_int, [Pitched, C.c_int, I3, I3, I3, C.c_double, C.c_void_p]),
     "sb_sqdiff": (C.c_int, [Pitched, Pitched, C.c_int, I3, I3, I3, C.c_void_p, C.c_void_p]),
     "sb_device_count": (C.c_int, [C.POINTER(C.c_int)]),

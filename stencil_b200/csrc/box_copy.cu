@@ -118,8 +118,13 @@ __global__ void __launch_bounds__(kCopyThreads) box_copy_single_kernel(const __g
   const unsigned total = seg.ny * seg.nz;
   for (unsigned long long row0 = (unsigned long long)blockIdx.x * rows_per_tile; row0 < total;
        row0 += (unsigned long long)gridDim.x * rows_per_tile) {
-    const unsigned left = total - (unsigned)row0;
-    copy_tile_dispatch(seg, (unsigned)row0, left < rows_per_tile ? left : rows_per_tile);
+    // NOTE: written as end = min(row0 + rpt, total); nrows = end - row0.  The natural
+    // min(total - row0, rpt) is miscompiled by ptxas 12.9 for sm_100a: the subtract and the minimum
+    // are fused into VIADDMNMX.U32 with the negation dropped (it computes min(row0 + total, rpt)),
+    // which turned every partial last tile into a full one (caught by tests/test_gpu_copy.py cases 7, 11).
+    const unsigned long long stop = row0 + rows_per_tile;
+    const unsigned end = stop < total ? (unsigned)stop : total;
+    copy_tile_dispatch(seg, (unsigned)row0, end - (unsigned)row0);
   }
 }
 

@@ -439,23 +439,16 @@ static int to_alloc_box(const sb_pitched &a, int dtype_size, const int64_t acc_o
   return SB_OK;
 }
 
-int sb_jacobi3d(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3],
-                const int64_t hi[3], const int64_t clo[3], const int64_t chi[3], void *stream) {
-  sb::JacobiParams p{};
-  int rc = to_alloc_box(src, dtype_size, acc_origin, lo, hi, p.lo, p.hi);
-  if (rc != SB_OK) return rc;
+static int jacobi_common(sb::JacobiParams &p, const sb_pitched &dst, const sb_pitched &src, int dtype_size,
+                         const int64_t acc_origin[3], const int64_t clo[3], const int64_t chi[3]) {
   if (!dst.ptr || dst.pitch != src.pitch || dst.ysize != src.ysize)
     return fail(SB_ERR_INVALID, "dst and src must have the same pitch and ysize");
-  for (int k = 0; k < 3; ++k) {
-    if (p.lo[k] < 1 && p.hi[k] > p.lo[k]) return fail(SB_ERR_INVALID, "region needs one ghost cell below it on axis %d", k);
-  }
   p.dst = static_cast<char *>(dst.ptr);
   p.src = static_cast<const char *>(src.ptr);
   p.pitch = src.pitch;
   p.slice = src.pitch * src.ysize;
   p.raw[0] = int(src.pitch / dtype_size);
   p.raw[1] = int(src.ysize);
-  p.raw[2] = p.hi[2] + 1; // planes: the caller guarantees plane hi.z (one ghost plane above) exists
   for (int k = 0; k < 3; ++k) p.org[k] = int(acc_origin[k]);
   // sphere placement, bin/jacobi3d.cu:46-51
   const int64_t ex = chi[0] - clo[0];
@@ -465,6 +458,63 @@ int sb_jacobi3d(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t ac
   p.cz = int((clo[2] + chi[2]) / 2);
   p.rad = int(ex / 10);
   p.zchunk = 0;
+  return SB_OK;
+}
+
+int sb_jacobi3d_regions(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], int n, const int64_t *lo,
+                        const int64_t *hi, const int64_t clo[3], const int64_t chi[3], void *stream) {
+  if (n < 0 || n > 8) return fail(SB_ERR_INVALID, "between 0 and 8 regions per launch");
+  sb::JacobiParams p{};
+  sb::JacobiRegions r{};
+  int zmax = 0;
+  r.first[0] = 0;
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    int alo[3], ahi[3];
+    int rc = to_alloc_box(src, dtype_size, acc_origin, lo + 3 * i, hi + 3 * i, alo, ahi);
+    if (rc != SB_OK) return rc;
+    long long cells = 1;
+    for (int k = 0; k < 3; ++k) {
+      if (ahi[k] > alo[k] && alo[k] < 1) return fail(SB_ERR_INVALID, "region needs one ghost cell below it on axis %d", k);
+      cells *= (ahi[k] > alo[k]) ? (ahi[k] - alo[k]) : 0;
+    }
+    if (cells == 0) continue;
+    if (cells >= (1ll << 32)) return fail(SB_ERR_INVALID, "region too large for sb_jacobi3d_regions");
+    for (int k = 0; k < 3; ++k) {
+      r.lo[m][k] = alo[k];
+      r.ext[m][k] = ahi[k] - alo[k];
+    }
+    if (ahi[2] > zmax) zmax = ahi[2];
+    r.first[m + 1] = r.first[m] + cells;
+    ++m;
+  }
+  r.n = m;
+  if (m == 0) return SB_OK;
+  int rc = jacobi_common(p, dst, src, dtype_size, acc_origin, clo, chi);
+  if (rc != SB_OK) return rc;
+  p.raw[2] = zmax + 1;
+  g_launches += uint64_t(sb::launch_jacobi_regions(p, r, dtype_size, static_cast<cudaStream_t>(stream)));
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+int sb_jacobi3d(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3],
+                const int64_t hi[3], const int64_t clo[3], const int64_t chi[3], void *stream) {
+  sb::JacobiParams p{};
+  int rc = to_alloc_box(src, dtype_size, acc_origin, lo, hi, p.lo, p.hi);
+  if (rc != SB_OK) return rc;
+  for (int k = 0; k < 3; ++k) {
+    if (p.lo[k] < 1 && p.hi[k] > p.lo[k]) return fail(SB_ERR_INVALID, "region needs one ghost cell below it on axis %d", k);
+  }
+  rc = jacobi_common(p, dst, src, dtype_size, acc_origin, clo, chi);
+  if (rc != SB_OK) return rc;
+  p.dst = static_cast<char *>(dst.ptr);
+  p.src = static_cast<const char *>(src.ptr);
+  p.pitch = src.pitch;
+  p.slice = src.pitch * src.ysize;
+  p.raw[0] = int(src.pitch / dtype_size);
+  p.raw[1] = int(src.ysize);
+  p.raw[2] = p.hi[2] + 1; // planes: the caller guarantees plane hi.z (one ghost plane above) exists
   const int n = sb::launch_jacobi(p, dtype_size, static_cast<cudaStream_t>(stream));
   g_launches += uint64_t(n);
   SB_CUDA(cudaGetLastError());

@@ -56,8 +56,14 @@ template <typename T> __device__ __forceinline__ T stencil_value(T px, T mx, T p
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// Register-blocked z-march (see the file header).  Everything that does not change along z is hoisted
+// out of the loop -- clamped row offsets, store masks, the (y - cy)^2 term of the sphere test -- so a
+// z-step is: RY centre loads for plane z+1, 2 halo-row loads and RY edge scalars for plane z, the
+// shuffles, 9 FP64 ops per cell and RY stores.  The loop is unrolled by three with the roles of the
+// three register planes rotating, so there are no register-to-register plane copies.
 template <typename T, int VX, int RY>
-__global__ void __launch_bounds__(256) jacobi_march_kernel(const __grid_constant__ JacobiParams p, int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(256, (RY <= 2 ? 3 : 2))
+    jacobi_march_kernel(const __grid_constant__ JacobiParams p, int tiles_x, int tiles_y) {
   using V = Vec<T, VX>;
   constexpr int WY = 8; // warps stacked in y
   const int lane = threadIdx.x & 31;
@@ -69,78 +75,83 @@ __global__ void __launch_bounds__(256) jacobi_march_kernel(const __grid_constant
   const int by = b % tiles_y;
   const int bz = b / tiles_y;
 
-  const int x = (p.lo[0] / VX) * VX + (bx * 32 + lane) * VX; // first cell of this lane (allocation index)
-  const int y = p.lo[1] + (by * WY + warp) * RY;             // first row of this warp
+  const int x0w = (p.lo[0] / VX) * VX + bx * 32 * VX;    // first cell of this warp's strip (allocation index)
+  const int x = x0w + lane * VX;                         // first cell of this lane
+  const int y = p.lo[1] + (by * WY + warp) * RY;         // first row of this warp
   const int z0 = p.lo[2] + bz * p.zchunk;
   const int z1 = min(z0 + p.zchunk, p.hi[2]);
-  if (y >= p.hi[1]) return;                                                  // warp-uniform
-  if ((p.lo[0] / VX) * VX + bx * 32 * VX >= p.hi[0]) return;                 // warp-uniform
+  if (y >= p.hi[1] || x0w >= p.hi[0]) return; // warp-uniform
 
-  const bool xin = (x + VX <= p.raw[0]); // vector lies inside the allocation row
-  const long long xoff = (long long)x * (long long)sizeof(T);
+  const long long S = p.slice, P = p.pitch;
+  const bool xin = (x + VX <= p.raw[0]); // this lane's vector lies inside the allocation row
+  const int xs = xin ? x : 0;            // out-of-row lanes read (and discard) column 0
+  const long long xoff = (long long)xs * (long long)sizeof(T);
 
-  auto row = [&](int yy, int zz) -> const char * {
-    yy = clampi(yy, 0, p.raw[1] - 1);
-    zz = clampi(zz, 0, p.raw[2] - 1);
-    return p.src + (long long)zz * p.slice + (long long)yy * p.pitch;
-  };
-  auto ldv = [&](const char *r) -> V {
-    V out;
-    if (xin) {
-      out = *reinterpret_cast<const V *>(r + xoff);
-    } else {
-#pragma unroll
-      for (int i = 0; i < VX; ++i) out.v[i] = T(0);
-    }
-    return out;
-  };
-
-  V prev[RY], cur[RY], nxt[RY];
-#pragma unroll
-  for (int j = 0; j < RY; ++j) {
-    prev[j] = ldv(row(y + j, z0 - 1));
-    cur[j] = ldv(row(y + j, z0));
-  }
-
-  // which scalar this lane fetches for the strip ends (lane 0: x-1, lane 31: x+VX)
+  // row byte offsets inside a plane; rows beyond the allocation are clamped (their results are masked)
+  auto yo = [&](int yy) { return (long long)clampi(yy, 0, p.raw[1] - 1) * P; };
+  const char *__restrict__ src = p.src;
+  const char *pc[RY]; // centre rows, plane z+1
+  const char *ph[RY]; // edge scalar of each row, plane z
+  char *pw[RY];       // output rows, plane z
   const bool edge_lane = (lane == 0) || (lane == 31);
   const int hx = clampi(lane == 0 ? x - 1 : x + VX, 0, p.raw[0] - 1);
-  const long long hoff = (long long)hx * (long long)sizeof(T);
+#pragma unroll
+  for (int j = 0; j < RY; ++j) {
+    pc[j] = src + (long long)(z0 + 1) * S + yo(y + j) + xoff;
+    ph[j] = src + (long long)z0 * S + yo(y + j) + (long long)hx * (long long)sizeof(T);
+    pw[j] = p.dst + (long long)z0 * S + (long long)(y + j) * P + (long long)x * (long long)sizeof(T);
+  }
+  const char *pu = src + (long long)z0 * S + yo(y - 1) + xoff;  // row above the strip, plane z
+  const char *pd = src + (long long)z0 * S + yo(y + RY) + xoff; // row below the strip, plane z
 
+  // store masks
+  bool row_ok[RY];
+#pragma unroll
+  for (int j = 0; j < RY; ++j) row_ok[j] = (y + j < p.hi[1]);
+  const bool full = (x >= p.lo[0]) && (x + VX <= p.hi[0]);
+  unsigned cell_ok = 0;
+#pragma unroll
+  for (int i = 0; i < VX; ++i)
+    if (x + i >= p.lo[0] && x + i < p.hi[0]) cell_ok |= 1u << i;
+
+  // sphere test pieces that are constant along z
   const int rr = (p.rad + 1) * (p.rad + 1);
+  int dy2[RY];
+#pragma unroll
+  for (int j = 0; j < RY; ++j) {
+    const int dyv = y + j + p.org[1] - p.cy;
+    dy2[j] = dyv * dyv;
+  }
+  const int gx0 = x + p.org[0];
 
-  for (int z = z0; z < z1; ++z) {
+  V A[RY], B[RY], C[RY];
 #pragma unroll
-    for (int j = 0; j < RY; ++j) nxt[j] = ldv(row(y + j, z + 1));
-    if (p.prefetch > 0 && xin) {
-      const int zp = z + 1 + p.prefetch;
-      if (zp < p.raw[2]) {
+  for (int j = 0; j < RY; ++j) {
+    A[j] = *reinterpret_cast<const V *>(pc[j] - 2 * S); // plane z0-1
+    B[j] = *reinterpret_cast<const V *>(pc[j] - S);     // plane z0
+  }
+  const int zlast = p.raw[2] - 1; // last plane that may be touched (prefetch guard)
+  int z = z0;
+
+  auto step = [&](const V(&prev)[RY], const V(&cur)[RY], V(&nxt)[RY]) {
 #pragma unroll
-        for (int j = 0; j < RY; ++j) {
-          const char *a = row(y + j, zp) + xoff;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-        }
-      }
+    for (int j = 0; j < RY; ++j) nxt[j] = *reinterpret_cast<const V *>(pc[j]);
+    if (p.prefetch > 0 && z + 1 + p.prefetch <= zlast) {
+#pragma unroll
+      for (int j = 0; j < RY; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc[j] + (long long)p.prefetch * S));
     }
-    const V up = ldv(row(y - 1, z));
-    const V dn = ldv(row(y + RY, z));
-
-    const int gz = z + p.org[2];
-    const int dz2 = (gz - p.cz) * (gz - p.cz);
-
+    const V up = *reinterpret_cast<const V *>(pu);
+    const V dn = *reinterpret_cast<const V *>(pd);
+    const int dzv = z + p.org[2] - p.cz;
+    const int dz2 = dzv * dzv;
 #pragma unroll
     for (int j = 0; j < RY; ++j) {
       T h = T(0);
-      if (edge_lane) h = *reinterpret_cast<const T *>(row(y + j, z) + hoff);
+      if (edge_lane) h = *reinterpret_cast<const T *>(ph[j]);
       T left = __shfl_up_sync(0xffffffffu, cur[j].v[VX - 1], 1);
       T right = __shfl_down_sync(0xffffffffu, cur[j].v[0], 1);
       if (lane == 0) left = h;
       if (lane == 31) right = h;
-
-      const int gy = y + j + p.org[1];
-      const int dyz2 = (gy - p.cy) * (gy - p.cy) + dz2;
-      const bool near_sphere = dyz2 < rr; // exact row pre-filter, see oracle/stencil_oracle.c
-
       V out;
 #pragma unroll
       for (int i = 0; i < VX; ++i) {
@@ -148,37 +159,45 @@ __global__ void __launch_bounds__(256) jacobi_march_kernel(const __grid_constant
         const T mx = (i > 0) ? cur[j].v[i > 0 ? i - 1 : 0] : left;
         const T py = (j < RY - 1) ? cur[j + 1 < RY ? j + 1 : j].v[i] : dn.v[i];
         const T my = (j > 0) ? cur[j > 0 ? j - 1 : 0].v[i] : up.v[i];
-        T val = stencil_value<T>(px, mx, py, my, nxt[j].v[i], prev[j].v[i]);
-        if (near_sphere) {
-          const int gx = x + i + p.org[0];
-          const int dh = (gx - p.hot_x) * (gx - p.hot_x) + dyz2;
-          const int dc = (gx - p.cold_x) * (gx - p.cold_x) + dyz2;
+        out.v[i] = stencil_value<T>(px, mx, py, my, nxt[j].v[i], prev[j].v[i]);
+      }
+      const int dyz2 = dy2[j] + dz2;
+      if (dyz2 < rr) { // rare: this row crosses a sphere (exact pre-filter, see oracle/stencil_oracle.c)
+#pragma unroll
+        for (int i = 0; i < VX; ++i) {
+          const int dh = (gx0 + i - p.hot_x) * (gx0 + i - p.hot_x) + dyz2;
+          const int dc = (gx0 + i - p.cold_x) * (gx0 + i - p.cold_x) + dyz2;
           if (in_sphere(dh, p.rad)) {
-            val = T(1);
+            out.v[i] = T(1);
           } else if (in_sphere(dc, p.rad)) {
-            val = T(0);
+            out.v[i] = T(0);
           }
         }
-        out.v[i] = val;
       }
-
-      if (y + j < p.hi[1]) {
-        char *drow = p.dst + (long long)z * p.slice + (long long)(y + j) * p.pitch;
-        if (x >= p.lo[0] && x + VX <= p.hi[0]) {
-          *reinterpret_cast<V *>(drow + xoff) = out;
+      if (row_ok[j]) {
+        if (full) {
+          *reinterpret_cast<V *>(pw[j]) = out;
         } else {
 #pragma unroll
-          for (int i = 0; i < VX; ++i) {
-            if (x + i >= p.lo[0] && x + i < p.hi[0]) reinterpret_cast<T *>(drow)[x + i] = out.v[i];
-          }
+          for (int i = 0; i < VX; ++i)
+            if (cell_ok & (1u << i)) reinterpret_cast<T *>(pw[j])[i] = out.v[i];
         }
       }
+      pc[j] += S;
+      ph[j] += S;
+      pw[j] += S;
     }
-#pragma unroll
-    for (int j = 0; j < RY; ++j) {
-      prev[j] = cur[j];
-      cur[j] = nxt[j];
-    }
+    pu += S;
+    pd += S;
+    ++z;
+  };
+
+  while (z < z1) {
+    step(A, B, C);
+    if (z >= z1) break;
+    step(B, C, A);
+    if (z >= z1) break;
+    step(C, A, B);
   }
 }
 
@@ -216,6 +235,55 @@ template <typename T> __global__ void __launch_bounds__(256) jacobi_cell_kernel(
       }
     }
     *reinterpret_cast<T *>(p.dst + (long long)z * p.slice + (long long)y * p.pitch + (long long)x * (long long)sizeof(T)) = val;
+  }
+}
+
+// All exterior slabs of a subdomain in one launch (bin/jacobi3d.cu:324-342 issues up to six).  One thread
+// per cell; inside a region threads run fastest along x when the slab is wide in x (coalesced rows)
+// and along y when it is an x-face (1..r cells wide), so a warp always touches few sectors per row.
+template <typename T>
+__global__ void __launch_bounds__(256) jacobi_regions_kernel(const __grid_constant__ JacobiParams p, const __grid_constant__ JacobiRegions rg) {
+  const long long total = rg.first[rg.n];
+  const int rr = (p.rad + 1) * (p.rad + 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = 0;
+    while (k + 1 < rg.n && i >= rg.first[k + 1]) ++k;
+    const unsigned li = (unsigned)(i - rg.first[k]);
+    const unsigned ex = rg.ext[k][0], ey = rg.ext[k][1];
+    unsigned xx, yy, zz;
+    if (ex >= 32) { // x fastest
+      xx = li % ex;
+      const unsigned t = li / ex;
+      yy = t % ey;
+      zz = t / ey;
+    } else { // y fastest
+      yy = li % ey;
+      const unsigned t = li / ey;
+      xx = t % ex;
+      zz = t / ex;
+    }
+    const int x = rg.lo[k][0] + (int)xx, y = rg.lo[k][1] + (int)yy, z = rg.lo[k][2] + (int)zz;
+    const long long off = (long long)z * p.slice + (long long)y * p.pitch + (long long)x * (long long)sizeof(T);
+    const char *c = p.src + off;
+    const T px = *reinterpret_cast<const T *>(c + sizeof(T));
+    const T mx = *reinterpret_cast<const T *>(c - sizeof(T));
+    const T py = *reinterpret_cast<const T *>(c + p.pitch);
+    const T my = *reinterpret_cast<const T *>(c - p.pitch);
+    const T pz = *reinterpret_cast<const T *>(c + p.slice);
+    const T mz = *reinterpret_cast<const T *>(c - p.slice);
+    T val = stencil_value<T>(px, mx, py, my, pz, mz);
+    const int gx = x + p.org[0], gy = y + p.org[1], gz = z + p.org[2];
+    const int dyz2 = (gy - p.cy) * (gy - p.cy) + (gz - p.cz) * (gz - p.cz);
+    if (dyz2 < rr) {
+      const int dh = (gx - p.hot_x) * (gx - p.hot_x) + dyz2;
+      const int dc = (gx - p.cold_x) * (gx - p.cold_x) + dyz2;
+      if (in_sphere(dh, p.rad)) {
+        val = T(1);
+      } else if (in_sphere(dc, p.rad)) {
+        val = T(0);
+      }
+    }
+    *reinterpret_cast<T *>(p.dst + off) = val;
   }
 }
 
@@ -289,6 +357,18 @@ int env_int(const char *name, int dflt) {
 
 } // namespace
 
+int launch_jacobi_regions(const JacobiParams &p, const JacobiRegions &r, int dtype_size, cudaStream_t stream) {
+  const long long total = r.first[r.n];
+  if (r.n <= 0 || total <= 0) return 0;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (dtype_size == 4)
+    jacobi_regions_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(p, r);
+  else
+    jacobi_regions_kernel<double><<<(unsigned)blocks, 256, 0, stream>>>(p, r);
+  return 1;
+}
+
 int launch_jacobi(const JacobiParams &p_in, int dtype_size, cudaStream_t stream) {
   JacobiParams p = p_in;
   const int ex = p.hi[0] - p.lo[0], ey = p.hi[1] - p.lo[1], ez = p.hi[2] - p.lo[2];
@@ -296,7 +376,7 @@ int launch_jacobi(const JacobiParams &p_in, int dtype_size, cudaStream_t stream)
 
   static const int ry = env_int("SB_JACOBI_RY", 2);
   static const int zchunk_env = env_int("SB_JACOBI_ZCHUNK", 0);
-  static const int pf = env_int("SB_JACOBI_PREFETCH", 4);
+  static const int pf = env_int("SB_JACOBI_PREFETCH", 2);
   static const int thin = env_int("SB_JACOBI_THIN_X", 16);
 
   if (ex < thin) {
@@ -314,7 +394,7 @@ int launch_jacobi(const JacobiParams &p_in, int dtype_size, cudaStream_t stream)
   if (zchunk_env > 0) {
     p.zchunk = zchunk_env;
   } else if (p.zchunk <= 0) {
-    p.zchunk = 64;
+    p.zchunk = 32;
   }
   if (p.zchunk > ez) p.zchunk = ez;
   p.prefetch = pf;

@@ -24,7 +24,16 @@ struct JacobiParams {
   int prefetch;  // L2 prefetch distance in planes (0 = off)
 };
 
+// Up to 8 thin regions (the exterior slabs of one subdomain) updated by ONE launch.
+struct JacobiRegions {
+  int n;
+  int lo[8][3];  // allocation-relative
+  int ext[8][3];
+  long long first[9]; // prefix sum of cell counts
+};
+
 // returns the number of kernel launches issued (0 if the region is empty)
+int launch_jacobi_regions(const JacobiParams &p, const JacobiRegions &r, int dtype_size, cudaStream_t stream);
 int launch_jacobi(const JacobiParams &p, int dtype_size, cudaStream_t stream);
 int launch_fill(char *dst, long long pitch, long long slice, const int lo[3], const int hi[3], int dtype_size, double value,
                 cudaStream_t stream);

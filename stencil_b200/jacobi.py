@@ -47,6 +47,7 @@ class Jacobi3D:
         interiors, exteriors = dd.get_interior(), dd.get_exterior()
         L = lib()
         self._fn = L.sb_jacobi3d
+        self._fn_regions = L.sb_jacobi3d_regions
         # calls[parity][domain] = (interior args, [exterior args...], whole args)
         self._calls = []
         for parity in (0, 1):
@@ -64,7 +65,11 @@ class Jacobi3D:
                 def pack(reg):
                     return (dst, src, d.elem_size(h.id), acc, i3(reg[0]), i3(reg[1]), clo, chi, s)
 
-                per_dom.append((pack(interiors[di]), [pack(r) for r in exteriors[di]], pack(d.get_compute_region())))
+                ne = len(exteriors[di])
+                elo = (C.c_int64 * (3 * max(ne, 1)))(*[v for r in exteriors[di] for v in r[0]])
+                ehi = (C.c_int64 * (3 * max(ne, 1)))(*[v for r in exteriors[di] for v in r[1]])
+                ext_pack = (dst, src, d.elem_size(h.id), acc, ne, elo, ehi, clo, chi, s)
+                per_dom.append((pack(interiors[di]), ext_pack, pack(d.get_compute_region())))
             self._calls.append(per_dom)
         self.interior_cells = sum(int(np.prod([hi[a] - lo[a] for a in range(3)])) for lo, hi in interiors)
         self._parity0 = dd._parity
@@ -77,9 +82,9 @@ class Jacobi3D:
             check(self._fn(*a[0]))
 
     def launch_exterior(self) -> None:
+        """All exterior slabs of a subdomain in ONE launch (the reference issues up to six)."""
         for a in self._args():
-            for e in a[1]:
-                check(self._fn(*e))
+            check(self._fn_regions(*a[1]))
 
     def launch_whole(self) -> None:
         for a in self._args():

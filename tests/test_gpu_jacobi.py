@@ -175,3 +175,26 @@ def test_jacobi_full_size_512_fp64_one_step():
     want = np.zeros(raw)
     co.jacobi_region(want, a, *args)
     assert np.array_equal(got[1:-1, 1:-1, 1:-1], want[1:-1, 1:-1, 1:-1])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fused_exterior_launch_matches_per_slab_launches(dtype):
+    """sb_jacobi3d_regions (all exterior slabs in one launch) == six sb_jacobi3d launches == oracle."""
+    n = (40, 36, 44)
+    origin = (40, 0, 44)
+    clo, chi = (0, 0, 0), (120, 36, 132)
+    ro = g.Radius.face_edge_corner(1, 0, 0)
+    raw = g.raw_size(n, ro)
+    rng = np.random.default_rng(19)
+    a = rng.random(raw[::-1]).astype(dtype)
+    src, dst = DevArray(a), DevArray(np.full(raw[::-1], 7, dtype=dtype))
+    acc = g.accessor_origin(origin, ro)
+    lo, hi = origin, tuple(origin[i] + n[i] for i in range(3))
+    slabs = g.get_exterior(lo, hi, ro)
+    elo = (C.c_int64 * 18)(*[v for s in slabs for v in s[0]])
+    ehi = (C.c_int64 * 18)(*[v for s in slabs for v in s[1]])
+    check(lib().sb_jacobi3d_regions(dst.pitched(), src.pitched(), a.dtype.itemsize, i3(acc), len(slabs), elo, ehi, i3(clo), i3(chi), None))
+    want = np.full(raw[::-1], 7, dtype=dtype)
+    for rlo, rhi in slabs:
+        co.jacobi_region(want, a, acc, rlo, rhi, clo, chi)
+    assert np.array_equal(dst.get(), want)
