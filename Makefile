@@ -86,7 +86,12 @@ bin/test_cpu: $(patsubst %,build/drv/t_%.o,$(TESTCPU)) $(LIBA)
 	@mkdir -p bin
 	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/t_%.o,$(TESTCPU)) $(LIBA)
 
-drivers: $(patsubst %,bin/%,$(DRIVERS)) bin/test_cuda bin/test_cpu
+# the baseline exchange driver (oracle/ref/ref_exchange_uniform.cu) against OUR library
+build/drv/exchange_uniform.o: oracle/ref/ref_exchange_uniform.cu $(wildcard include/stencil/*)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(DRVFLAGS) -c $< -o $@
+
+drivers: $(patsubst %,bin/%,$(DRIVERS)) bin/test_cuda bin/test_cpu bin/exchange_uniform
 
 oracle:
 	$(MAKE) -C oracle

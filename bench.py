@@ -280,8 +280,7 @@ def run_ours(args, rank, world):
             dd.exchange()
             jac.launch_whole()
             k1[i].record(cs0)
-        for s in jac.streams:
-            s.synchronize()
+        jac.synchronize()
         dd.swap()
     ev_b.record(cs0)
     barrier()

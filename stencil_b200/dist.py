@@ -187,3 +187,113 @@ class RemoteDomains:
 
 def share_domains(dd, w: World) -> RemoteDomains:
     return RemoteDomains(dd, w)
+
+
+# --------------------------------------------------------------------------------------------- NCCL fallback
+def messages_from(dd, src_rank: int) -> List[dict]:
+    """The send plan of ANY rank (pure geometry: every rank can compute every other rank's plan)."""
+    from .domain import ALL_DIRS, get_neighbor, halo_extent, halo_pos
+
+    part, radius = dd.partition_, dd.radius_
+    out = []
+    for idx in part.indices():
+        rank, slot = dd._owner[idx]
+        if rank != src_rank:
+            continue
+        sz = part.subdomain_size(idx)
+        for d in ALL_DIRS:
+            nd = (-d[0], -d[1], -d[2])
+            if radius.dir(nd) == 0:
+                continue
+            dst_idx = get_neighbor(idx, d, part.dim)
+            dst_sz = part.subdomain_size(dst_idx)
+            ext = halo_extent(nd, dst_sz, radius)
+            if ext[0] * ext[1] * ext[2] == 0:
+                continue
+            out.append(
+                dict(src_idx=idx, src_slot=slot, dst_idx=dst_idx, dst_rank=dd._owner[dst_idx][0], dst_slot=dd._owner[dst_idx][1], dir=d,
+                     src_pos=halo_pos(d, sz, radius, False), dst_pos=halo_pos(nd, dst_sz, radius, True), ext=ext)
+            )
+    return out
+
+
+def wire_order(msgs: List[dict]) -> List[dict]:
+    """Sender and receiver agree on one order per (src rank -> dst rank) buffer: larger messages first, ties by
+    (src subdomain, direction) -- Message::by_size of the reference (tx_common.hpp:25-36) extended to several
+    subdomains per rank."""
+    return sorted(msgs, key=lambda m: (-(m["ext"][0] * m["ext"][1] * m["ext"][2]), m["src_idx"], m["dir"]))
+
+
+class NcclExchange:
+    """Fallback transport where CUDA IPC / peer mapping between two ranks' GPUs is unavailable (or when forced with
+    SB_FORCE_NCCL=1): pack -> ncclSend/ncclRecv (torch.distributed P2P ops, one group per exchange) -> unpack, with the
+    reference's packed wire format (src/packer.cu: per message, per quantity, offset aligned to the element size).
+    This is the analogue of the reference's CudaAwareMpiSender/Recver (tx_cuda.cuh:769-930); it costs two extra HBM
+    passes per halo byte compared with the fused direct write and is never used when P2P works."""
+
+    def __init__(self, dd, w: World):
+        import torch
+
+        from .domain import CopyPlan, box_copy
+
+        self.dd, self.w = dd, w
+        self.dev = dd.domains_[0].gpu()
+        es = [d for d in dd.domains_[0].elem_sizes_]
+
+        def layout(msgs):
+            off, entries = 0, []
+            for m in wire_order(msgs):
+                n = m["ext"][0] * m["ext"][1] * m["ext"][2]
+                for q, e in enumerate(es):
+                    off = (off + e - 1) & ~(e - 1)
+                    entries.append((m, q, off))
+                    off += n * e
+            return off, entries
+
+        mine = messages_from(dd, w.rank)
+        self.peers = sorted({m["dst_rank"] for m in mine} - {w.rank})
+        self.send_buf, self.recv_buf, self.pack, self.unpack = {}, {}, {}, {}
+        for b in self.peers:
+            out_total, out_entries = layout([m for m in mine if m["dst_rank"] == b])
+            in_total, in_entries = layout([m for m in messages_from(dd, b) if m["dst_rank"] == w.rank])
+            self.send_buf[b] = torch.empty(max(out_total, 1), dtype=torch.uint8, device=f"cuda:{self.dev}")
+            self.recv_buf[b] = torch.empty(max(in_total, 1), dtype=torch.uint8, device=f"cuda:{self.dev}")
+            self.pack[b], self.unpack[b] = [], []
+            for parity in (0, 1):
+                pk, up = [], []
+                for m, q, off in out_entries:
+                    d = dd.domains_[m["src_slot"]]
+                    src = Pitched((d._curr0 if parity == 0 else d._next0)[q], d.raw_size()[0] * es[q], d.raw_size()[1])
+                    dense = Pitched(self.send_buf[b].data_ptr() + off, m["ext"][0] * es[q], m["ext"][1])
+                    pk.append(box_copy(dense, (0, 0, 0), src, m["src_pos"], m["ext"], es[q]))
+                for m, q, off in in_entries:
+                    d = dd.domains_[m["dst_slot"]]
+                    dst = Pitched((d._curr0 if parity == 0 else d._next0)[q], d.raw_size()[0] * es[q], d.raw_size()[1])
+                    dense = Pitched(self.recv_buf[b].data_ptr() + off, m["ext"][0] * es[q], m["ext"][1])
+                    up.append(box_copy(dst, m["dst_pos"], dense, (0, 0, 0), m["ext"], es[q]))
+                self.pack[b].append(CopyPlan(self.dev, pk))
+                self.unpack[b].append(CopyPlan(self.dev, up))
+        self.bytes_per_exchange = sum(t.numel() for t in self.send_buf.values())
+
+    def exchange(self, parity: int, stream) -> None:
+        import torch
+        import torch.distributed as td
+
+        with torch.cuda.stream(stream):
+            for b in self.peers:
+                self.pack[b][parity].launch(stream)
+            ops = []
+            for b in self.peers:
+                ops.append(td.P2POp(td.isend, self.send_buf[b], b))
+                ops.append(td.P2POp(td.irecv, self.recv_buf[b], b))
+            if ops:
+                for r in td.batch_isend_irecv(ops):
+                    r.wait()
+            for b in self.peers:
+                self.unpack[b][parity].launch(stream)
+
+    def close(self) -> None:
+        for plans in list(self.pack.values()) + list(self.unpack.values()):
+            for p in plans:
+                p.destroy()
+        self.pack, self.unpack = {}, {}

@@ -378,7 +378,9 @@ class DistributedDomain:
         self._streams = []
         self._bytes_kernel = 0
         self._bytes_peer = 0
-        self._dist = None  # multi-process state (see dist.py)
+        self._remote = None  # CUDA-IPC mappings of the other ranks (dist.RemoteDomains)
+        self._nccl = None  # NCCL fallback (dist.NcclExchange)
+        self._use_nccl = False
         self._epoch = 0
 
     # -- configuration (call before realize)
@@ -459,6 +461,7 @@ class DistributedDomain:
         # one node: NodePartition(size, radius, 1 node, n_sub gpus)  (partition.hpp:157-211)
         self.partition_ = Partition(self.size_, self.radius_, 1, n_sub, trivial=trivial)
         self._world = world
+        self._assign_owners()
 
     def realize(self) -> None:
         from . import dist as _dist
@@ -467,11 +470,6 @@ class DistributedDomain:
         world = self._world
         part = self.partition_
         all_idx = part.indices()
-        # subdomain i of the node lives on (rank, local gpu slot): rank-major, like the reference's
-        # global id = node*gpusPerNode + id with an identity placement (NVSwitch is uniform, so the
-        # QAP of partition.hpp:706-716 is permutation-invariant -- DESIGN.md)
-        per_rank = len(self.gpus_)
-        self._owner = {idx: (k // per_rank, k % per_rank) for k, idx in enumerate(all_idx)}
         my = [idx for idx in all_idx if self._owner[idx][0] == world.rank]
         for slot, idx in enumerate(my):
             d = LocalDomain(part.subdomain_size(idx), part.subdomain_origin(idx), self.gpus_[slot])
@@ -488,8 +486,25 @@ class DistributedDomain:
                 check(lib().sb_enable_peer(a, b, C.byref(ok)))
                 if not ok.value:
                     raise _lib.StencilError(f"GPU {a} cannot map GPU {b}: P2P unavailable (NCCL fallback not selected)")
-        self._remote = _dist.share_domains(self, world) if world.size > 1 else None
+        self._remote, self._nccl = None, None
+        if world.size > 1:
+            import os
+
+            force_nccl = os.environ.get("SB_FORCE_NCCL", "0") == "1"
+            if not force_nccl:
+                try:
+                    self._remote = _dist.share_domains(self, world)
+                except _lib.StencilError as e:  # no IPC / peer mapping between these GPUs
+                    import warnings
+
+                    warnings.warn(f"CUDA IPC mapping unavailable ({e}); falling back to NCCL send/recv")
+                    force_nccl = True
+            self._use_nccl = force_nccl
+        else:
+            self._use_nccl = False
         self._build_plans()
+        if self._use_nccl:
+            self._nccl = _dist.NcclExchange(self, world)
         import torch
 
         self._streams = [torch.cuda.Stream(device=d.gpu(), priority=-1) for d in self.domains_]
@@ -507,35 +522,69 @@ class DistributedDomain:
             return Pitched(base, raw[0] * d.elem_size(q), raw[1]), d.gpu()
         return self._remote.pitched(idx, q, parity)
 
-    def _build_plans(self) -> None:
+    def plan_messages(self) -> List[dict]:
+        """The send plan of this rank (pure geometry, no GPU): one entry per (local subdomain, direction)
+        with a non-zero receiving radius -- src/stencil.cu:327-412.  dict(src_slot, src_idx, dst_idx,
+        dst_rank, dst_slot, dir, src_pos, dst_pos, ext)."""
         part = self.partition_
+        my = [idx for idx in part.indices() if self._owner[idx][0] == self._world.rank]
+        out = []
+        for slot, idx in enumerate(my):
+            sz = part.subdomain_size(idx)
+            for dirv in ALL_DIRS:
+                if self.radius_.dir(_neg(dirv)) == 0:
+                    continue  # src/stencil.cu:344
+                dst_idx = get_neighbor(idx, dirv, part.dim)
+                dst_sz = part.subdomain_size(dst_idx)
+                ext = halo_extent(_neg(dirv), dst_sz, self.radius_)  # stencil.cu:361-363
+                if ext[0] * ext[1] * ext[2] == 0:
+                    continue
+                out.append(
+                    dict(
+                        src_slot=slot,
+                        src_idx=idx,
+                        dst_idx=dst_idx,
+                        dst_rank=self._owner[dst_idx][0],
+                        dst_slot=self._owner[dst_idx][1],
+                        dir=dirv,
+                        src_pos=halo_pos(dirv, sz, self.radius_, False),
+                        dst_pos=halo_pos(_neg(dirv), dst_sz, self.radius_, True),
+                        ext=ext,
+                    )
+                )
+        return out
+
+    def _assign_owners(self) -> None:
+        # subdomain k of the node (linear order of the partition) lives on (rank, local gpu slot),
+        # rank-major: the reference's global id = node*gpusPerNode + id with an identity placement
+        # (NVSwitch is uniform, so the QAP of partition.hpp:706-716 is permutation-invariant -- DESIGN.md)
+        per_rank = len(self.gpus_)
+        self._owner = {idx: (k // per_rank, k % per_rank) for k, idx in enumerate(self.partition_.indices())}
+
+    def _build_plans(self) -> None:
         for d in self.domains_:
             d._curr0, d._next0 = list(d.curr_), list(d.next_)
         self._plans = []
         self._bytes_kernel = self._bytes_peer = 0
+        msgs = self.plan_messages()
         for parity in (0, 1):
             plans = []
             for di, d in enumerate(self.domains_):
-                idx = self.domain_idx_[di]
                 copies: List[BoxCopy] = []
-                for dirv in ALL_DIRS:
-                    if self.radius_.dir(_neg(dirv)) == 0:
-                        continue  # src/stencil.cu:344
-                    dst_idx = get_neighbor(idx, dirv, part.dim)
-                    dst_sz = part.subdomain_size(dst_idx)
-                    ext = halo_extent(_neg(dirv), dst_sz, self.radius_)  # stencil.cu:361-363
-                    if ext[0] * ext[1] * ext[2] == 0:
+                for m in msgs:
+                    if m["src_slot"] != di:
                         continue
-                    src_pos = d.halo_pos(dirv, False)
-                    dst_pos = halo_pos(_neg(dirv), dst_sz, self.radius_, True)
-                    for q in range(d.num_data()):
-                        src_p, _ = self._pitched_of(idx, q, parity)
-                        dst_p, dst_dev = self._pitched_of(dst_idx, q, parity)
-                        copies.append(box_copy(dst_p, dst_pos, src_p, src_pos, ext, d.elem_size(q)))
+                    if self._use_nccl and m["dst_rank"] != self._world.rank:
                         if parity == 0:
-                            nbytes = d.elem_size(q) * ext[0] * ext[1] * ext[2]
-                            same = self._owner[dst_idx][0] == self._world.rank and dst_dev == d.gpu()
-                            if same:
+                            self._bytes_peer += sum(d.elem_size(q) for q in range(d.num_data())) * m["ext"][0] * m["ext"][1] * m["ext"][2]
+                        continue  # carried by the NCCL fallback, not by the fused kernel
+                    for q in range(d.num_data()):
+                        src_p, _ = self._pitched_of(m["src_idx"], q, parity)
+                        dst_p, dst_dev = self._pitched_of(m["dst_idx"], q, parity)
+                        copies.append(box_copy(dst_p, m["dst_pos"], src_p, m["src_pos"], m["ext"], d.elem_size(q)))
+                        if parity == 0:
+                            nbytes = d.elem_size(q) * m["ext"][0] * m["ext"][1] * m["ext"][2]
+                            if m["dst_rank"] == self._world.rank and dst_dev == d.gpu():
                                 self._bytes_kernel += nbytes
                             else:
                                 self._bytes_peer += nbytes
@@ -553,6 +602,8 @@ class DistributedDomain:
             plan.launch(s)
         if self._remote is not None:
             self._remote.finish(self._epoch, self._streams)
+        if self._nccl is not None:
+            self._nccl.exchange(self._parity, self._streams[0])
 
     def exchange(self) -> None:
         """DistributedDomain::exchange (src/stencil.cu:1002-1186): returns when every ghost cell of
@@ -580,6 +631,9 @@ class DistributedDomain:
         if self._remote is not None:
             self._remote.close()
             self._remote = None
+        if getattr(self, "_nccl", None) is not None:
+            self._nccl.close()
+            self._nccl = None
         for d in self.domains_:
             d.free()
         self.domains_ = []

@@ -44,6 +44,9 @@ class Jacobi3D:
         self.dd, self.h, self.overlap = dd, h, overlap
         self.creg = dd.get_compute_region()
         self.streams = [torch.cuda.Stream(device=d.gpu()) for d in dd.domains()]
+        # the exterior slabs only depend on the exchange, not on the interior kernel: they run on their
+        # own stream so that they (and their launch latency) hide behind the interior kernel's tail
+        self.ext_streams = [torch.cuda.Stream(device=d.gpu()) for d in dd.domains()]
         interiors, exteriors = dd.get_interior(), dd.get_exterior()
         L = lib()
         self._fn = L.sb_jacobi3d
@@ -68,7 +71,7 @@ class Jacobi3D:
                 ne = len(exteriors[di])
                 elo = (C.c_int64 * (3 * max(ne, 1)))(*[v for r in exteriors[di] for v in r[0]])
                 ehi = (C.c_int64 * (3 * max(ne, 1)))(*[v for r in exteriors[di] for v in r[1]])
-                ext_pack = (dst, src, d.elem_size(h.id), acc, ne, elo, ehi, clo, chi, s)
+                ext_pack = (dst, src, d.elem_size(h.id), acc, ne, elo, ehi, clo, chi, stream_ptr(self.ext_streams[di]))
                 per_dom.append((pack(interiors[di]), ext_pack, pack(d.get_compute_region())))
             self._calls.append(per_dom)
         self.interior_cells = sum(int(np.prod([hi[a] - lo[a] for a in range(3)])) for lo, hi in interiors)
@@ -100,9 +103,16 @@ class Jacobi3D:
         else:
             dd.exchange()
             self.launch_whole()
+        self.synchronize()
+        dd.swap()
+
+    def synchronize(self) -> None:
+        """Wait for the compute streams (bin/jacobi3d.cu:363-365)."""
         for s in self.streams:
             s.synchronize()
-        dd.swap()
+        if self.overlap:
+            for s in self.ext_streams:
+                s.synchronize()
 
     def init(self, value: float = 0.5) -> None:
         """init_kernel (bin/jacobi3d.cu:18-29) on curr; ghost cells are filled by the first exchange."""

@@ -125,3 +125,23 @@ def test_multi_gpu_in_process_if_available():
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     run_exchange_check((32, 24, 20), make_radius("c2"), list(range(n)), [np.float32, np.float64], no.hash_field, n_exchanges=2, swap_between=True)
+
+
+@pytest.mark.parametrize("mode", ["ipc", "nccl"])
+def test_one_process_per_gpu_if_available(mode):
+    """torchrun with one rank per GPU: CUDA-IPC direct write (default) and the NCCL fallback."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    n = min(torch.cuda.device_count(), 8)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SB_FORCE_NCCL="1" if mode == "nccl" else "0")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533" if mode == "ipc" else "29534", os.path.join(root, "tests", "mp_exchange_check.py")]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "mp_exchange_check OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
