@@ -64,8 +64,18 @@ private:
   Method flags_;
   PlacementStrategy strategy_;
 
-  // the fused exchange: plans_[parity][local domain]; parity = number of swap() calls mod 2
+  // the fused exchange: plans_[parity][local domain]; parity = number of swap() calls mod 2.
+  // Phase 1 (plans_): each subdomain stores its outgoing halos into the neighbours' ghost cells -- except
+  // thin rows bound for ANOTHER GPU (x-faces, x-edges, corners), which are packed into a dense staging
+  // buffer in the neighbour's memory (one tiny NVLink transaction per 8-byte row is what kills both the
+  // exchange and the concurrently running compute kernel).  Phase 2 (unpackPlans_): each receiver
+  // scatters its staging buffers into its ghost cells.
   std::vector<sb_copy_plan *> plans_[2];
+  std::vector<sb_copy_plan *> unpackPlans_[2];       // nullptr where a subdomain receives nothing staged
+  std::vector<std::vector<size_t>> stageSenders_;    // per receiver: local domains that stage into it
+  std::vector<void *> stagingBufs_;                  // device allocations (on the receivers' GPUs)
+  std::vector<int> stagingDevs_;
+  std::vector<cudaEvent_t> phase1Done_;              // one per local domain
   std::vector<RcStream> streams_; // one high-priority stream per local domain
   int parity_;
 

@@ -72,11 +72,25 @@ DistributedDomain::~DistributedDomain() {
 }
 
 void DistributedDomain::destroy_plans() {
-  for (auto &side : plans_) {
-    for (sb_copy_plan *p : side)
-      if (p) sb_copy_plan_destroy(p);
-    side.clear();
+  for (auto *sides : {&plans_, &unpackPlans_}) {
+    for (int parity = 0; parity < 2; ++parity) {
+      for (sb_copy_plan *p : (*sides)[parity])
+        if (p) sb_copy_plan_destroy(p);
+      (*sides)[parity].clear();
+    }
   }
+  for (size_t i = 0; i < stagingBufs_.size(); ++i) {
+    cudaSetDevice(stagingDevs_[i]);
+    cudaFree(stagingBufs_[i]);
+  }
+  stagingBufs_.clear();
+  stagingDevs_.clear();
+  for (size_t i = 0; i < phase1Done_.size(); ++i) {
+    cudaSetDevice(domains_[i].gpu());
+    cudaEventDestroy(phase1Done_[i]);
+  }
+  phase1Done_.clear();
+  stageSenders_.clear();
 }
 
 void DistributedDomain::set_methods(Method flags) noexcept {
@@ -154,65 +168,132 @@ void DistributedDomain::plan_exchange() {
     planFile << di << ":cuda" << domains_[di].gpu() << ":" << domainIdx_[di] << " sz=" << domains_[di].size() << "\n";
   planFile << "\n== fused direct-write messages ==\n";
 
+  // ---- the message list (geometry only) ----------------------------------------------------------
+  struct Msg {
+    size_t src, dst; // local domain ids
+    Dim3 dir, srcPos, dstPos, ext;
+  };
+  std::vector<Msg> msgs;
+  for (size_t di = 0; di < domains_.size(); ++di) {
+    const LocalDomain &src = domains_[di];
+    for (int z = -1; z <= 1; ++z) {
+      for (int y = -1; y <= 1; ++y) {
+        for (int x = -1; x <= 1; ++x) {
+          const Dim3 dir(x, y, z);
+          if (Dim3(0, 0, 0) == dir) continue;
+          // the neighbour on side dir needs our cells only if ITS stencil reaches back (-dir)
+          if (0 == radius_.dir(dir * -1)) continue;
+          const Topology::OptionalNeighbor nbr = topology_.get_neighbor(domainIdx_[di], dir);
+          if (!nbr.exists) continue;
+          const int dstRank = placement_->get_rank(nbr.index);
+          if (dstRank != rank_) {
+            LOG_FATAL("subdomain " << nbr.index << " lives on rank " << dstRank
+                                   << ": the C++ API drives one rank x N GPUs; use the one-process-per-GPU "
+                                      "CUDA-IPC mode of stencil_b200 (python) for multi-process runs");
+          }
+          const size_t dj = size_t(placement_->get_subdomain_id(nbr.index));
+          const LocalDomain &dst = domains_[dj];
+          const Dim3 ext = LocalDomain::halo_extent(dir * -1, dst.size(), radius_);
+          if (0 == ext.flatten()) continue;
+
+          // attribute the bytes the way the reference's planner picks a transport
+          uint64_t *bucket = nullptr;
+          const char *how = "";
+          if (any_methods(Method::CudaKernel) && src.gpu() == dst.gpu()) {
+            bucket = &numBytesCudaKernel_;
+            how = "same-gpu";
+          } else if (any_methods(Method::CudaMemcpyPeer) && gpu_topo::peer(src.gpu(), dst.gpu())) {
+            bucket = &numBytesCudaMemcpyPeer_;
+            how = "peer";
+          } else if (any_methods(Method::CudaMpi)) {
+            bucket = &numBytesCudaMpi_;
+            how = "self-mpi";
+          } else {
+            LOG_FATAL("No method available to send required message " << dir << "\n");
+          }
+          if (!gpu_topo::peer(src.gpu(), dst.gpu())) {
+            LOG_FATAL("GPU " << src.gpu() << " cannot map GPU " << dst.gpu() << " (no P2P): unsupported on this path");
+          }
+          uint64_t msgBytes = 0;
+          for (int64_t q = 0; q < src.num_data(); ++q) msgBytes += uint64_t(src.elem_size(size_t(q))) * ext.flatten();
+          *bucket += msgBytes;
+          planFile << di << "->" << dj << " " << dir << " " << msgBytes << "B " << how << "\n";
+          msgs.push_back(Msg{di, dj, dir, src.halo_pos(dir, false), dst.halo_pos(dir * -1, true), ext});
+        }
+      }
+    }
+  }
+
+  // ---- staging buffers: thin rows that cross GPUs ----------------------------------------------------
+  constexpr int64_t kStageMaxRowBytes = 64;
+  struct Staged {
+    size_t msg;
+    int64_t q;
+    int64_t offset;
+  };
+  // per (src, dst) pair: buffer + entries
+  std::map<std::pair<size_t, size_t>, std::vector<Staged>> stagedOf;
+  std::map<std::pair<size_t, size_t>, int64_t> stagedBytes;
+  for (size_t mi = 0; mi < msgs.size(); ++mi) {
+    const Msg &m = msgs[mi];
+    if (domains_[m.src].gpu() == domains_[m.dst].gpu()) continue;
+    for (int64_t q = 0; q < domains_[m.src].num_data(); ++q) {
+      const int64_t es = int64_t(domains_[m.src].elem_size(size_t(q)));
+      if (m.ext.x * es >= kStageMaxRowBytes) continue;
+      const auto key = std::make_pair(m.src, m.dst);
+      int64_t &off = stagedBytes[key];
+      off = (off + 15) & ~int64_t(15);
+      stagedOf[key].push_back(Staged{mi, q, off});
+      off += es * int64_t(m.ext.flatten());
+    }
+  }
+  std::map<std::pair<size_t, size_t>, char *> stageBuf;
+  stageSenders_.assign(domains_.size(), {});
+  for (const auto &kv : stagedBytes) {
+    const size_t dj = kv.first.second;
+    void *buf = nullptr;
+    CUDA_RUNTIME(cudaSetDevice(domains_[dj].gpu()));
+    CUDA_RUNTIME(cudaMalloc(&buf, size_t(kv.second)));
+    stagingBufs_.push_back(buf);
+    stagingDevs_.push_back(domains_[dj].gpu());
+    stageBuf[kv.first] = static_cast<char *>(buf);
+    stageSenders_[dj].push_back(kv.first.first);
+  }
+  for (size_t di = 0; di < domains_.size(); ++di) {
+    cudaEvent_t ev;
+    CUDA_RUNTIME(cudaSetDevice(domains_[di].gpu()));
+    CUDA_RUNTIME(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    phase1Done_.push_back(ev);
+  }
+
+  // ---- the two plans per subdomain and swap parity -----------------------------------------------------
   for (int parity = 0; parity < 2; ++parity) {
     for (size_t di = 0; di < domains_.size(); ++di) {
       const LocalDomain &src = domains_[di];
       std::vector<sb_box_copy> copies;
-      for (int z = -1; z <= 1; ++z) {
-        for (int y = -1; y <= 1; ++y) {
-          for (int x = -1; x <= 1; ++x) {
-            const Dim3 dir(x, y, z);
-            if (Dim3(0, 0, 0) == dir) continue;
-            // the neighbour on side dir needs our cells only if ITS stencil reaches back (-dir)
-            if (0 == radius_.dir(dir * -1)) continue;
-            const Topology::OptionalNeighbor nbr = topology_.get_neighbor(domainIdx_[di], dir);
-            if (!nbr.exists) continue;
-            const int dstRank = placement_->get_rank(nbr.index);
-            if (dstRank != rank_) {
-              LOG_FATAL("subdomain " << nbr.index << " lives on rank " << dstRank
-                                     << ": the C++ API drives one rank x N GPUs; use the one-process-per-GPU "
-                                        "CUDA-IPC mode of stencil_b200 (python) for multi-process runs");
-            }
-            const LocalDomain &dst = domains_[size_t(placement_->get_subdomain_id(nbr.index))];
-            const Dim3 ext = LocalDomain::halo_extent(dir * -1, dst.size(), radius_);
-            if (0 == ext.flatten()) continue;
-
-            // attribute the bytes the way the reference's planner picks a transport
-            uint64_t *bucket = nullptr;
-            const char *how = "";
-            if (any_methods(Method::CudaKernel) && src.gpu() == dst.gpu()) {
-              bucket = &numBytesCudaKernel_;
-              how = "same-gpu";
-            } else if (any_methods(Method::CudaMemcpyPeer) && gpu_topo::peer(src.gpu(), dst.gpu())) {
-              bucket = &numBytesCudaMemcpyPeer_;
-              how = "peer";
-            } else if (any_methods(Method::CudaMpi)) {
-              bucket = &numBytesCudaMpi_;
-              how = "self-mpi";
-            } else {
-              LOG_FATAL("No method available to send required message " << dir << "\n");
-            }
-            if (!gpu_topo::peer(src.gpu(), dst.gpu())) {
-              LOG_FATAL("GPU " << src.gpu() << " cannot map GPU " << dst.gpu() << " (no P2P): unsupported on this path");
-            }
-
-            uint64_t msgBytes = 0;
-            for (int64_t q = 0; q < src.num_data(); ++q) {
-              sb_box_copy c{};
-              c.src = as_sb(0 == parity ? src.curr_data(size_t(q)) : src.next_data(size_t(q)));
-              c.dst = as_sb(0 == parity ? dst.curr_data(size_t(q)) : dst.next_data(size_t(q)));
-              set3(c.src_pos, src.halo_pos(dir, false));
-              set3(c.dst_pos, dst.halo_pos(dir * -1, true));
-              set3(c.extent, ext);
-              c.elem_size = int64_t(src.elem_size(size_t(q)));
-              copies.push_back(c);
-              msgBytes += uint64_t(c.elem_size) * ext.flatten();
-            }
-            if (0 == parity) {
-              *bucket += msgBytes;
-              planFile << di << "->" << placement_->get_subdomain_id(nbr.index) << " " << dir << " " << msgBytes << "B " << how << "\n";
-            }
+      for (size_t mi = 0; mi < msgs.size(); ++mi) {
+        const Msg &m = msgs[mi];
+        if (m.src != di) continue;
+        const LocalDomain &dst = domains_[m.dst];
+        const auto key = std::make_pair(m.src, m.dst);
+        for (int64_t q = 0; q < src.num_data(); ++q) {
+          sb_box_copy c{};
+          c.elem_size = int64_t(src.elem_size(size_t(q)));
+          c.src = as_sb(0 == parity ? src.curr_data(size_t(q)) : src.next_data(size_t(q)));
+          set3(c.src_pos, m.srcPos);
+          set3(c.extent, m.ext);
+          const Staged *st = nullptr;
+          auto it = stagedOf.find(key);
+          if (it != stagedOf.end())
+            for (const Staged &cand : it->second)
+              if (cand.msg == mi && cand.q == q) st = &cand;
+          if (st) { // dense staging buffer in the receiver's memory
+            c.dst = sb_pitched{stageBuf[key] + st->offset, m.ext.x * c.elem_size, m.ext.y};
+          } else {
+            c.dst = as_sb(0 == parity ? dst.curr_data(size_t(q)) : dst.next_data(size_t(q)));
+            set3(c.dst_pos, m.dstPos);
           }
+          copies.push_back(c);
         }
       }
       sb_copy_plan *plan = nullptr;
@@ -220,6 +301,27 @@ void DistributedDomain::plan_exchange() {
         LOG_FATAL("exchange plan: " << sb_last_error());
       }
       plans_[parity].push_back(plan);
+
+      // phase 2 of this subdomain as a receiver
+      std::vector<sb_box_copy> scatter;
+      for (const auto &kv : stagedOf) {
+        if (kv.first.second != di) continue;
+        for (const Staged &st : kv.second) {
+          const Msg &m = msgs[st.msg];
+          sb_box_copy c{};
+          c.elem_size = int64_t(src.elem_size(size_t(st.q)));
+          c.src = sb_pitched{stageBuf[kv.first] + st.offset, m.ext.x * c.elem_size, m.ext.y};
+          c.dst = as_sb(0 == parity ? src.curr_data(size_t(st.q)) : src.next_data(size_t(st.q)));
+          set3(c.dst_pos, m.dstPos);
+          set3(c.extent, m.ext);
+          scatter.push_back(c);
+        }
+      }
+      sb_copy_plan *up = nullptr;
+      if (!scatter.empty() && SB_OK != sb_copy_plan_create(&up, src.gpu(), scatter.data(), int64_t(scatter.size()))) {
+        LOG_FATAL("exchange scatter plan: " << sb_last_error());
+      }
+      unpackPlans_[parity].push_back(up);
     }
   }
   planFile.close();
@@ -262,9 +364,26 @@ const Rect3 DistributedDomain::get_compute_region() const noexcept { return Rect
 void DistributedDomain::exchange_async() {
   nvtxRangePush("DD::exchange_async");
   const std::vector<sb_copy_plan *> &plans = plans_[parity_];
+  const std::vector<sb_copy_plan *> &scatter = unpackPlans_[parity_];
+  bool anyStaged = false;
   for (size_t di = 0; di < plans.size(); ++di) {
     if (SB_OK != sb_copy_plan_launch(plans[di], streams_[di])) {
       LOG_FATAL("exchange: " << sb_last_error());
+    }
+    anyStaged = anyStaged || (scatter[di] != nullptr);
+  }
+  if (anyStaged) {
+    for (size_t di = 0; di < plans.size(); ++di) {
+      CUDA_RUNTIME(cudaSetDevice(domains_[di].gpu()));
+      CUDA_RUNTIME(cudaEventRecord(phase1Done_[di], streams_[di]));
+    }
+    for (size_t di = 0; di < plans.size(); ++di) {
+      if (!scatter[di]) continue;
+      CUDA_RUNTIME(cudaSetDevice(domains_[di].gpu()));
+      for (size_t sj : stageSenders_[di]) CUDA_RUNTIME(cudaStreamWaitEvent(streams_[di], phase1Done_[sj], 0));
+      if (SB_OK != sb_copy_plan_launch(scatter[di], streams_[di])) {
+        LOG_FATAL("exchange scatter: " << sb_last_error());
+      }
     }
   }
   nvtxRangePop();

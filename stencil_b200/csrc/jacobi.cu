@@ -61,9 +61,16 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // z-step is: RY centre loads for plane z+1, 2 halo-row loads and RY edge scalars for plane z, the
 // shuffles, 9 FP64 ops per cell and RY stores.  The loop is unrolled by three with the roles of the
 // three register planes rotating, so there are no register-to-register plane copies.
-template <typename T, int VX, int RY, int MB>
+//
+// SHIFT variant (RY = 1): when the row pitch is only half-vector aligned (FP32 rows of 514 floats =
+// 2056 B are 8 mod 16) consecutive rows alternate between two 16-byte phases.  Each warp then
+// starts its strip VX/2 cells earlier on the odd-phase rows, so the HBM-facing accesses (centre
+// loads, stores) stay full 128-bit vectors on every row; only the two L1-resident neighbour rows
+// (y-1, y+1), which have the opposite phase, are fetched as two half vectors.
+template <typename T, int VX, int RY, int MB, bool SHIFT>
 __global__ void __launch_bounds__(256, MB)
     jacobi_march_kernel(const __grid_constant__ JacobiParams p, int tiles_x, int tiles_y) {
+  static_assert(!SHIFT || (RY == 1 && VX >= 2), "the phase-shifted variant handles one row per warp");
   using V = Vec<T, VX>;
   constexpr int WY = 8; // warps stacked in y
   const int lane = threadIdx.x & 31;
@@ -75,16 +82,20 @@ __global__ void __launch_bounds__(256, MB)
   const int by = b % tiles_y;
   const int bz = b / tiles_y;
 
-  const int x0w = (p.lo[0] / VX) * VX + bx * 32 * VX;    // first cell of this warp's strip (allocation index)
-  const int x = x0w + lane * VX;                         // first cell of this lane
+  const long long S = p.slice, P = p.pitch;
   const int y = p.lo[1] + (by * WY + warp) * RY;         // first row of this warp
+  // phase of this row inside a 16-byte vector, in elements (0 unless SHIFT)
+  const int shift = SHIFT ? (int)((((unsigned long long)y * (unsigned long long)P) & (sizeof(T) * VX - 1)) / sizeof(T)) : 0;
+  const int x0w = (p.lo[0] / VX) * VX + bx * 32 * VX - shift; // first cell of this warp's strip (allocation index)
+  const int x = x0w + lane * VX;                              // first cell of this lane
   const int z0 = p.lo[2] + bz * p.zchunk;
   const int z1 = min(z0 + p.zchunk, p.hi[2]);
   if (y >= p.hi[1] || x0w >= p.hi[0]) return; // warp-uniform
 
-  const long long S = p.slice, P = p.pitch;
-  const bool xin = (x + VX <= p.raw[0]); // this lane's vector lies inside the allocation row
-  const int xs = xin ? x : 0;            // out-of-row lanes read (and discard) column 0
+  // does this lane's vector lie inside the allocation row?  (SHIFT: a vector may hang over either end
+  // of its row into the neighbouring row of the same allocation -- valid memory, masked cells)
+  const bool xin = SHIFT ? true : (x + VX <= p.raw[0]);
+  const int xs = xin ? x : 0; // out-of-row lanes read (and discard) column 0
   const long long xoff = (long long)xs * (long long)sizeof(T);
 
   // row byte offsets inside a plane; rows beyond the allocation are clamped (their results are masked)
@@ -140,8 +151,22 @@ __global__ void __launch_bounds__(256, MB)
 #pragma unroll
       for (int j = 0; j < RY; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc[j] + (long long)p.prefetch * S));
     }
-    const V up = *reinterpret_cast<const V *>(pu);
-    const V dn = *reinterpret_cast<const V *>(pd);
+    V up, dn;
+    if (SHIFT) { // the rows above / below have the other phase: two aligned half vectors each
+      using H = Vec<T, (VX >= 2 ? VX / 2 : 1)>;
+      const H u0 = reinterpret_cast<const H *>(pu)[0], u1 = reinterpret_cast<const H *>(pu)[1];
+      const H d0 = reinterpret_cast<const H *>(pd)[0], d1 = reinterpret_cast<const H *>(pd)[1];
+#pragma unroll
+      for (int i = 0; i < VX / 2; ++i) {
+        up.v[i] = u0.v[i];
+        up.v[i + VX / 2] = u1.v[i];
+        dn.v[i] = d0.v[i];
+        dn.v[i + VX / 2] = d1.v[i];
+      }
+    } else {
+      up = *reinterpret_cast<const V *>(pu);
+      dn = *reinterpret_cast<const V *>(pd);
+    }
     const int dzv = z + p.org[2] - p.cz;
     const int dz2 = dzv * dzv;
 #pragma unroll
@@ -326,9 +351,10 @@ __global__ void __launch_bounds__(256) sqdiff_kernel(const char *a, const char *
   }
 }
 
-template <typename T, int VX> int launch_march(const JacobiParams &p, int ry, int mb, cudaStream_t stream) {
+template <typename T, int VX, bool SHIFT> int launch_march(const JacobiParams &p, int ry, int mb, cudaStream_t stream) {
   const int x0a = (p.lo[0] / VX) * VX;
-  const int tiles_x = (p.hi[0] - x0a + 32 * VX - 1) / (32 * VX);
+  // a shifted row starts VX/2 cells early, so the last tile must reach VX/2 cells further
+  const int tiles_x = (p.hi[0] - x0a + (SHIFT ? VX / 2 : 0) + 32 * VX - 1) / (32 * VX);
   const int ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
   const int tiles_z = (nz + p.zchunk - 1) / p.zchunk;
   auto go = [&](auto kern, int RY) {
@@ -337,25 +363,32 @@ template <typename T, int VX> int launch_march(const JacobiParams &p, int ry, in
     kern<<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
   };
   // (rows per warp, min CTAs/SM): fewer rows -> fewer registers -> more warps in flight
+  if (SHIFT) {
+    if (mb == 5)
+      go(jacobi_march_kernel<T, VX, 1, 5, SHIFT>, 1);
+    else
+      go(jacobi_march_kernel<T, VX, 1, 4, SHIFT>, 1);
+    return 1;
+  }
   const int key = ry * 10 + mb;
   switch (key) {
   case 14:
-    go(jacobi_march_kernel<T, VX, 1, 4>, 1);
+    go(jacobi_march_kernel<T, VX, 1, 4, false>, 1);
     break;
   case 15:
-    go(jacobi_march_kernel<T, VX, 1, 5>, 1);
+    go(jacobi_march_kernel<T, VX, 1, 5, false>, 1);
     break;
   case 16:
-    go(jacobi_march_kernel<T, VX, 1, 6>, 1);
+    go(jacobi_march_kernel<T, VX, 1, 6, false>, 1);
     break;
   case 24:
-    go(jacobi_march_kernel<T, VX, 2, 4>, 2);
+    go(jacobi_march_kernel<T, VX, 2, 4, false>, 2);
     break;
   case 42:
-    go(jacobi_march_kernel<T, VX, 4, 2>, 4);
+    go(jacobi_march_kernel<T, VX, 4, 2, false>, 4);
     break;
   default:
-    go(jacobi_march_kernel<T, VX, 2, 3>, 2);
+    go(jacobi_march_kernel<T, VX, 2, 3, false>, 2);
     break;
   }
   return 1;
@@ -411,15 +444,20 @@ int launch_jacobi(const JacobiParams &p_in, int dtype_size, cudaStream_t stream)
   if (p.zchunk > ez) p.zchunk = ez;
   p.prefetch = pf;
 
-  const unsigned long long a = (unsigned long long)(uintptr_t)p.src | (unsigned long long)(uintptr_t)p.dst |
-                               (unsigned long long)p.pitch | (unsigned long long)p.slice;
+  const unsigned long long base = (unsigned long long)(uintptr_t)p.src | (unsigned long long)(uintptr_t)p.dst | (unsigned long long)p.slice;
+  const unsigned long long a = base | (unsigned long long)p.pitch;
+  static const int allow_shift = env_int("SB_JACOBI_SHIFT", 1);
+  // rows whose pitch is a multiple of half a vector only: phase-shifted full vectors (see the kernel)
+  const bool half_phase = allow_shift && (base % 16 == 0) && (p.pitch % 16 == 8);
   if (dtype_size == 8) {
-    if (a % 16 == 0) return launch_march<double, 2>(p, ry, mb, stream);
-    return launch_march<double, 1>(p, ry, mb, stream);
+    if (a % 16 == 0) return launch_march<double, 2, false>(p, ry, mb, stream);
+    if (half_phase) return launch_march<double, 2, true>(p, ry, mb, stream);
+    return launch_march<double, 1, false>(p, ry, mb, stream);
   }
-  if (a % 16 == 0) return launch_march<float, 4>(p, ry, mb, stream);
-  if (a % 8 == 0) return launch_march<float, 2>(p, ry, mb, stream);
-  return launch_march<float, 1>(p, ry, mb, stream);
+  if (a % 16 == 0) return launch_march<float, 4, false>(p, ry, mb, stream);
+  if (half_phase) return launch_march<float, 4, true>(p, ry, mb, stream);
+  if (a % 8 == 0) return launch_march<float, 2, false>(p, ry, mb, stream);
+  return launch_march<float, 1, false>(p, ry, mb, stream);
 }
 
 int launch_fill(char *dst, long long pitch, long long slice, const int lo[3], const int hi[3], int dtype_size, double value,

@@ -77,6 +77,7 @@ class RemoteDomains:
         mine = {
             "rank": w.rank,
             "flags": export(self.flags),
+            "recv": {key: export(ptr) for key, ptr in dd._recv_local.items()},
             "domains": {
                 dd.domain_idx_[i]: {
                     "raw": d.raw_size(),
@@ -97,11 +98,15 @@ class RemoteDomains:
 
         self.remote: Dict[Vec, dict] = {}
         self.peer_flags: Dict[int, int] = {}
+        self.recv: Dict[tuple, int] = {}  # (src_idx, dst_idx) -> staging buffer in the DST rank's memory
         for info in everyone:
             r = info["rank"]
             if r == w.rank:
                 continue
             self.peer_flags[r] = open_(info["flags"])
+            for key, h in info["recv"].items():
+                if dd._owner[tuple(key[0])][0] == w.rank:  # only buffers one of my subdomains writes into
+                    self.recv[(tuple(key[0]), tuple(key[1]))] = open_(h)
             for idx, dom in info["domains"].items():
                 self.remote[tuple(idx)] = {
                     "raw": tuple(dom["raw"]),
@@ -215,6 +220,32 @@ def messages_from(dd, src_rank: int) -> List[dict]:
                      src_pos=halo_pos(d, sz, radius, False), dst_pos=halo_pos(nd, dst_sz, radius, True), ext=ext)
             )
     return out
+
+
+STAGE_MAX_ROW_BYTES = 64
+
+
+def staging_layout(dd, src_idx, dst_idx):
+    """Messages from subdomain src_idx to subdomain dst_idx (on a DIFFERENT GPU) whose rows are shorter than
+    STAGE_MAX_ROW_BYTES (x-faces, x-edges, corners): storing such rows straight into the peer's ghost cells costs one
+    tiny NVLink transaction per row (measured on 2x B200: 1.6 M 8-byte remote stores = 194 us and a 70 % slower
+    interior kernel), so the sender packs them into ONE dense receive buffer in the peer's memory (contiguous 128-byte
+    NVLink packets) and the receiver scatters them locally.  Pure geometry: both sides compute the same layout.
+    Returns (total_bytes, [dict(dir, q, offset, ext, src_pos, dst_pos, es)])."""
+    es = [int(e) for e in dd._elem_sizes()]
+    entries, off = [], 0
+    src_rank = dd._owner[tuple(src_idx)][0]
+    for m in messages_from(dd, src_rank):
+        if tuple(m["src_idx"]) != tuple(src_idx) or tuple(m["dst_idx"]) != tuple(dst_idx):
+            continue
+        n = m["ext"][0] * m["ext"][1] * m["ext"][2]
+        for q, e in enumerate(es):
+            if m["ext"][0] * e >= STAGE_MAX_ROW_BYTES:
+                continue
+            off = (off + 15) & ~15
+            entries.append(dict(dir=m["dir"], q=q, offset=off, ext=m["ext"], src_pos=m["src_pos"], dst_pos=m["dst_pos"], es=e))
+            off += n * e
+    return off, entries
 
 
 def wire_order(msgs: List[dict]) -> List[dict]:

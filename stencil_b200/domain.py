@@ -26,6 +26,7 @@ from __future__ import annotations
 import ctypes as C
 import enum
 import itertools
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -487,9 +488,8 @@ class DistributedDomain:
                 if not ok.value:
                     raise _lib.StencilError(f"GPU {a} cannot map GPU {b}: P2P unavailable (NCCL fallback not selected)")
         self._remote, self._nccl = None, None
+        self._alloc_staging()
         if world.size > 1:
-            import os
-
             force_nccl = os.environ.get("SB_FORCE_NCCL", "0") == "1"
             if not force_nccl:
                 try:
@@ -521,6 +521,46 @@ class DistributedDomain:
             raw = d.raw_size()
             return Pitched(base, raw[0] * d.elem_size(q), raw[1]), d.gpu()
         return self._remote.pitched(idx, q, parity)
+
+    def _elem_sizes(self) -> List[int]:
+        return [dt.itemsize for dt in self.dtypes_]
+
+    def _gpu_key(self, idx: Vec):
+        """Identity of the GPU holding subdomain idx (for 'same GPU?' decisions)."""
+        rank, slot = self._owner[tuple(idx)]
+        if rank == self._world.rank:
+            return (rank, self.gpus_[slot])
+        return (rank, -1 - slot)
+
+    def _alloc_staging(self) -> None:
+        """Receive buffers (on MY GPUs) for the thin messages other GPUs send to my subdomains (dist.staging_layout)."""
+        from . import dist as _dist
+
+        self._recv_local: Dict[tuple, int] = {}
+        self._recv_entries: Dict[tuple, list] = {}
+        if os.environ.get("SB_NO_STAGING", "0") == "1":
+            return
+        for di, dst_idx in enumerate(self.domain_idx_):
+            srcs = {get_neighbor(dst_idx, d, self.partition_.dim) for d in ALL_DIRS}
+            for src_idx in sorted(srcs):
+                if self._gpu_key(src_idx) == self._gpu_key(dst_idx):
+                    continue
+                total, entries = _dist.staging_layout(self, src_idx, dst_idx)
+                if total == 0:
+                    continue
+                p = C.c_void_p()
+                check(lib().sb_malloc(C.byref(p), total, self.domains_[di].gpu()))
+                self._recv_local[(tuple(src_idx), tuple(dst_idx))] = int(p.value)
+                self._recv_entries[(tuple(src_idx), tuple(dst_idx))] = entries
+
+    def _staging_target(self, src_idx: Vec, dst_idx: Vec):
+        """Address of the staging buffer for (src -> dst), wherever dst lives; None if this pair is not staged."""
+        key = (tuple(src_idx), tuple(dst_idx))
+        if key in self._recv_local:
+            return self._recv_local[key]
+        if self._remote is not None and key in self._remote.recv:
+            return self._remote.recv[key]
+        return None
 
     def plan_messages(self) -> List[dict]:
         """The send plan of this rank (pure geometry, no GPU): one entry per (local subdomain, direction)
@@ -562,48 +602,110 @@ class DistributedDomain:
         self._owner = {idx: (k // per_rank, k % per_rank) for k, idx in enumerate(self.partition_.indices())}
 
     def _build_plans(self) -> None:
+        """Phase 1 (one launch per local subdomain): every outgoing halo region is stored either straight into the
+        neighbour's ghost cells (same GPU, or wide rows over NVLink) or, for thin rows bound for another GPU, into
+        the neighbour's dense staging buffer.  Phase 2 (one launch per local subdomain that has staged senders):
+        scatter the staging buffers into the ghost cells."""
+        from . import dist as _dist
+
         for d in self.domains_:
             d._curr0, d._next0 = list(d.curr_), list(d.next_)
-        self._plans = []
+        self._plans, self._unpack_plans = [], []
         self._bytes_kernel = self._bytes_peer = 0
+        self._staged_bytes = 0
         msgs = self.plan_messages()
         for parity in (0, 1):
-            plans = []
+            plans, unplans = [], []
             for di, d in enumerate(self.domains_):
                 copies: List[BoxCopy] = []
                 for m in msgs:
                     if m["src_slot"] != di:
                         continue
-                    if self._use_nccl and m["dst_rank"] != self._world.rank:
+                    remote = m["dst_rank"] != self._world.rank
+                    if self._use_nccl and remote:
                         if parity == 0:
                             self._bytes_peer += sum(d.elem_size(q) for q in range(d.num_data())) * m["ext"][0] * m["ext"][1] * m["ext"][2]
                         continue  # carried by the NCCL fallback, not by the fused kernel
+                    stage_base = None if self._gpu_key(m["src_idx"]) == self._gpu_key(m["dst_idx"]) else self._staging_target(m["src_idx"], m["dst_idx"])
+                    staged = {}
+                    if stage_base is not None:
+                        _, entries = _dist.staging_layout(self, m["src_idx"], m["dst_idx"])
+                        staged = {e["q"]: e for e in entries if e["dir"] == m["dir"]}
                     for q in range(d.num_data()):
+                        es = d.elem_size(q)
                         src_p, _ = self._pitched_of(m["src_idx"], q, parity)
-                        dst_p, dst_dev = self._pitched_of(m["dst_idx"], q, parity)
-                        copies.append(box_copy(dst_p, m["dst_pos"], src_p, m["src_pos"], m["ext"], d.elem_size(q)))
+                        nbytes = es * m["ext"][0] * m["ext"][1] * m["ext"][2]
+                        if q in staged:
+                            dense = Pitched(stage_base + staged[q]["offset"], m["ext"][0] * es, m["ext"][1])
+                            copies.append(box_copy(dense, (0, 0, 0), src_p, m["src_pos"], m["ext"], es))
+                            if parity == 0:
+                                self._staged_bytes += nbytes
+                        else:
+                            dst_p, _ = self._pitched_of(m["dst_idx"], q, parity)
+                            copies.append(box_copy(dst_p, m["dst_pos"], src_p, m["src_pos"], m["ext"], es))
                         if parity == 0:
-                            nbytes = d.elem_size(q) * m["ext"][0] * m["ext"][1] * m["ext"][2]
-                            if m["dst_rank"] == self._world.rank and dst_dev == d.gpu():
+                            if self._gpu_key(m["src_idx"]) == self._gpu_key(m["dst_idx"]):
                                 self._bytes_kernel += nbytes
                             else:
                                 self._bytes_peer += nbytes
                 plans.append(CopyPlan(d.gpu(), copies))
+                # phase 2 of this subdomain as a receiver
+                ucopies: List[BoxCopy] = []
+                for (src_idx, dst_idx), base in self._recv_local.items():
+                    if dst_idx != tuple(self.domain_idx_[di]):
+                        continue
+                    for e in self._recv_entries[(src_idx, dst_idx)]:
+                        dst_p, _ = self._pitched_of(dst_idx, e["q"], parity)
+                        dense = Pitched(base + e["offset"], e["ext"][0] * e["es"], e["ext"][1])
+                        ucopies.append(box_copy(dst_p, e["dst_pos"], dense, (0, 0, 0), e["ext"], e["es"]))
+                unplans.append(CopyPlan(d.gpu(), ucopies) if ucopies else None)
             self._plans.append(plans)
+            self._unpack_plans.append(unplans)
+        # in-process senders of each local receiver (for the phase-1 -> phase-2 stream dependency)
+        self._stage_senders: List[List[int]] = []
+        for di, dst_idx in enumerate(self.domain_idx_):
+            snd = set()
+            for (src_idx, d_idx) in self._recv_local:
+                if d_idx == tuple(dst_idx) and self._owner[src_idx][0] == self._world.rank:
+                    snd.add(self._owner[src_idx][1])
+            self._stage_senders.append(sorted(snd))
 
     # -- the hot path
     def exchange_async(self) -> None:
-        """Launch the fused halo write of every local subdomain on its high-priority stream."""
-        plans = self._plans[self._parity]
+        """Enqueue the halo exchange on the library's high-priority streams (one per local subdomain)."""
+        import torch
+
+        plans, unplans = self._plans[self._parity], self._unpack_plans[self._parity]
         if self._remote is not None:
             self._epoch += 1
             self._remote.begin(self._epoch, self._streams)
         for plan, s in zip(plans, self._streams):
             plan.launch(s)
         if self._remote is not None:
-            self._remote.finish(self._epoch, self._streams)
+            self._remote.finish(self._epoch, self._streams)  # every remote sender's phase 1 has landed
+            if len(self._streams) > 1:
+                ev0 = torch.cuda.Event()
+                ev0.record(self._streams[0])
+                for o in self._streams[1:]:
+                    o.wait_event(ev0)
         if self._nccl is not None:
             self._nccl.exchange(self._parity, self._streams[0])
+        # phase 2: scatter what other GPUs staged for my subdomains
+        if any(u is not None for u in unplans):
+            events = {}
+            for di, snd in enumerate(self._stage_senders):
+                for sj in snd:
+                    if sj not in events and sj != di:
+                        ev = torch.cuda.Event()
+                        ev.record(self._streams[sj])
+                        events[sj] = ev
+            for di, u in enumerate(unplans):
+                if u is None:
+                    continue
+                for sj in self._stage_senders[di]:
+                    if sj != di:
+                        self._streams[di].wait_event(events[sj])
+                u.launch(self._streams[di])
 
     def exchange(self) -> None:
         """DistributedDomain::exchange (src/stencil.cu:1002-1186): returns when every ghost cell of
@@ -624,25 +726,40 @@ class DistributedDomain:
         self._parity ^= 1
 
     def close(self) -> None:
-        for plans in self._plans:
+        for plans in self._plans + getattr(self, "_unpack_plans", []):
             for p in plans:
-                p.destroy()
-        self._plans = []
+                if p is not None:
+                    p.destroy()
+        self._plans, self._unpack_plans = [], []
+
         if self._remote is not None:
             self._remote.close()
             self._remote = None
         if getattr(self, "_nccl", None) is not None:
             self._nccl.close()
             self._nccl = None
+        # staging buffers: only after every peer has unmapped them (barrier inside RemoteDomains.close)
+        for ptr in getattr(self, "_recv_local", {}).values():
+            lib().sb_free(C.c_void_p(ptr), self.domains_[0].gpu() if self.domains_ else 0)
+        self._recv_local = {}
         for d in self.domains_:
             d.free()
         self.domains_ = []
 
 
 # ------------------------------------------------------------------------------------------ jacobi helpers
+def _set_current_device(dev: int) -> None:
+    """LocalDomain::set_device: kernels launched on a stream need that stream's device to be current."""
+    import torch
+
+    if torch.cuda.current_device() != dev:
+        torch.cuda.set_device(dev)
+
+
 def jacobi3d(d: LocalDomain, h: DataHandle, region: Tuple[Vec, Vec], compute_region: Tuple[Vec, Vec], stream=None) -> None:
     """One application of the reference's stencil_kernel (bin/jacobi3d.cu:40-85) to `region` of
     subdomain d: reads curr, writes next."""
+    _set_current_device(d.gpu())
     check(
         lib().sb_jacobi3d(
             d.next_data(h.id),
@@ -660,6 +777,7 @@ def jacobi3d(d: LocalDomain, h: DataHandle, region: Tuple[Vec, Vec], compute_reg
 
 def fill(d: LocalDomain, h: DataHandle, region: Tuple[Vec, Vec], value: float, which: str = "curr", stream=None) -> None:
     """init_kernel (bin/jacobi3d.cu:18-29)."""
+    _set_current_device(d.gpu())
     check(
         lib().sb_fill(d.pitched(h.id, which), d.elem_size(h.id), i3(d.accessor_origin()), i3(region[0]), i3(region[1]), float(value), stream_ptr(stream))
     )

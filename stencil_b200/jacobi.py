@@ -74,6 +74,11 @@ class Jacobi3D:
                 ext_pack = (dst, src, d.elem_size(h.id), acc, ne, elo, ehi, clo, chi, stream_ptr(self.ext_streams[di]))
                 per_dom.append((pack(interiors[di]), ext_pack, pack(d.get_compute_region())))
             self._calls.append(per_dom)
+        # like the reference driver (d.set_device() before every launch, bin/jacobi3d.cu:310), the CUDA device
+        # must be current when launching on one of its streams; only matters with several GPUs per process
+        self._devs = [d.gpu() for d in dd.domains()]
+        self._multi_dev = len(set(self._devs)) > 1
+        self._set_device = torch.cuda.set_device
         self.interior_cells = sum(int(np.prod([hi[a] - lo[a] for a in range(3)])) for lo, hi in interiors)
         self._parity0 = dd._parity
 
@@ -81,16 +86,22 @@ class Jacobi3D:
         return self._calls[(self.dd._parity - self._parity0) & 1]
 
     def launch_interior(self) -> None:
-        for a in self._args():
+        for dev, a in zip(self._devs, self._args()):
+            if self._multi_dev:
+                self._set_device(dev)
             check(self._fn(*a[0]))
 
     def launch_exterior(self) -> None:
         """All exterior slabs of a subdomain in ONE launch (the reference issues up to six)."""
-        for a in self._args():
+        for dev, a in zip(self._devs, self._args()):
+            if self._multi_dev:
+                self._set_device(dev)
             check(self._fn_regions(*a[1]))
 
     def launch_whole(self) -> None:
-        for a in self._args():
+        for dev, a in zip(self._devs, self._args()):
+            if self._multi_dev:
+                self._set_device(dev)
             check(self._fn(*a[2]))
 
     def step(self) -> None:
