@@ -91,7 +91,25 @@ build/drv/exchange_uniform.o: oracle/ref/ref_exchange_uniform.cu $(wildcard incl
 	@mkdir -p $(dir $@)
 	$(NVCC) $(DRVFLAGS) -c $< -o $@
 
-drivers: $(patsubst %,bin/%,$(DRIVERS)) bin/test_cuda bin/test_cpu bin/exchange_uniform
+# our own multi-GPU check of the C++ API
+build/drv/test_exchange_multigpu.o: tests/cpp/test_exchange_multigpu.cu $(wildcard include/stencil/*)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(DRVFLAGS) -c $< -o $@
+
+# the reference's astaroth driver (its own MHD kernels; halos through our library), unchanged
+ASTRO     := astaroth kernels astaroth_utils
+ASTROFLAGS := $(filter-out -I$(REF)/bin,$(DRVFLAGS)) --use_fast_math -I$(REF)/astaroth -DAC_DEFAULT_CONFIG=\"oracle/_ref/astaroth.conf\"
+build/drv/astro_%.o: $(REF)/astaroth/%.cu $(wildcard include/stencil/*)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(ASTROFLAGS) -c $< -o $@
+build/drv/astro_statistics.o: $(REF)/astaroth/statistics.cpp
+	@mkdir -p $(dir $@)
+	$(NVCC) $(ASTROFLAGS) -c $< -o $@
+bin/astaroth: $(patsubst %,build/drv/astro_%.o,$(ASTRO)) build/drv/astro_statistics.o $(LIBA)
+	@mkdir -p bin
+	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/astro_%.o,$(ASTRO)) build/drv/astro_statistics.o $(LIBA)
+
+drivers: $(patsubst %,bin/%,$(DRIVERS)) bin/test_cuda bin/test_cpu bin/exchange_uniform bin/astaroth bin/test_exchange_multigpu
 
 oracle:
 	$(MAKE) -C oracle

@@ -48,7 +48,16 @@ done
 # our own baseline driver over the reference library (uniform radii only, see the file header)
 compile "$HERE/ref_exchange_uniform.cu" "$OBJ/ref_exchange_uniform.o"
 $NVCC $LINK -o "$OUT/ref_exchange_uniform" "$OBJ/ref_exchange_uniform.o" "$OBJ/bin_statistics.o" "${LIBOBJS[@]}" "$OBJ/mpi_shim.o"
-# ... and the same source against OUR library, for a like-for-like number
+# the reference's astaroth driver against the reference library (+ its config file, data only)
+AFLAGS="${FLAGS/-I$REF\/bin/} --use_fast_math -I$REF/astaroth -DAC_DEFAULT_CONFIG=\"oracle/_ref/astaroth.conf\""
+pids=()
+for f in astaroth.cu kernels.cu astaroth_utils.cu statistics.cpp; do
+  compile_a() { if [ ! -f "$2" ] || [ "$1" -nt "$2" ]; then $NVCC $AFLAGS -c "$1" -o "$2"; fi; }
+  compile_a "$REF/astaroth/$f" "$OBJ/astro_${f%.*}.o" & pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+$NVCC $LINK -o "$OUT/ref_astaroth" "$OBJ/astro_astaroth.o" "$OBJ/astro_kernels.o" "$OBJ/astro_astaroth_utils.o" "$OBJ/astro_statistics.o" "${LIBOBJS[@]}" "$OBJ/mpi_shim.o"
+cp "$REF/astaroth/astaroth.conf" "$OUT/astaroth.conf"
 
 # the reference's own test suites
 pids=(); TC=(); TH=()

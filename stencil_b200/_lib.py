@@ -60,6 +60,7 @@ _SIGS = {
     "sb_copy_plan_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sb_copy_plan_bytes": (C.c_int64, [C.c_void_p]),
     "sb_copy_plan_num_tiles": (C.c_int64, [C.c_void_p]),
+    "sb_copy_plan_num_tma_segments": (C.c_int64, [C.c_void_p]),
     "sb_copy_plan_destroy": (C.c_int, [C.c_void_p]),
     "sb_signal": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_int, C.c_void_p]),
     "sb_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p]),

@@ -339,6 +339,7 @@ class CopyPlan:
         self.device = device
         self.bytes = int(lib().sb_copy_plan_bytes(h))
         self.num_tiles = int(lib().sb_copy_plan_num_tiles(h))
+        self.num_tma_segments = int(lib().sb_copy_plan_num_tma_segments(h))
 
     def launch(self, stream=None) -> None:
         check(lib().sb_copy_plan_launch(self._h, stream_ptr(stream)))
@@ -500,6 +501,8 @@ class DistributedDomain:
                     warnings.warn(f"CUDA IPC mapping unavailable ({e}); falling back to NCCL send/recv")
                     force_nccl = True
             self._use_nccl = force_nccl
+            if force_nccl:
+                self._drop_remote_staging()
         else:
             self._use_nccl = False
         self._build_plans()
@@ -531,6 +534,12 @@ class DistributedDomain:
         if rank == self._world.rank:
             return (rank, self.gpus_[slot])
         return (rank, -1 - slot)
+
+    def _drop_remote_staging(self) -> None:
+        """NCCL mode: messages from other ranks arrive packed through NCCL, not through staging buffers."""
+        for key in [k for k in self._recv_local if self._owner[k[0]][0] != self._world.rank]:
+            lib().sb_free(C.c_void_p(self._recv_local.pop(key)), self.domains_[0].gpu())
+            self._recv_entries.pop(key)
 
     def _alloc_staging(self) -> None:
         """Receive buffers (on MY GPUs) for the thin messages other GPUs send to my subdomains (dist.staging_layout)."""
