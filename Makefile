@@ -10,7 +10,7 @@ NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall 
 INC       := -Iinclude -Istencil_b200/csrc
 
 # ---- core: kernels + C ABI (shared library, loaded by python and linked by the C++ API)
-CSRC      := stencil_b200/csrc/box_copy.cu stencil_b200/csrc/jacobi.cu stencil_b200/csrc/capi.cu
+CSRC      := stencil_b200/csrc/box_copy.cu stencil_b200/csrc/jacobi.cu stencil_b200/csrc/astaroth.cu stencil_b200/csrc/capi.cu
 COBJ      := $(patsubst stencil_b200/csrc/%.cu,build/csrc/%.o,$(CSRC))
 SO        := stencil_b200/libstencil_b200.so
 
@@ -109,7 +109,15 @@ bin/astaroth: $(patsubst %,build/drv/astro_%.o,$(ASTRO)) build/drv/astro_statist
 	@mkdir -p bin
 	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/astro_%.o,$(ASTRO)) build/drv/astro_statistics.o $(LIBA)
 
-drivers: $(patsubst %,bin/%,$(DRIVERS)) bin/test_cuda bin/test_cpu bin/exchange_uniform bin/astaroth bin/test_exchange_multigpu
+# the same driver with the reference's kernels.cu REPLACED by ours (src/astaroth_kernels.cu -> sb_astaroth_substep)
+build/drv/astro_b200_kernels.o: src/astaroth_kernels.cu include/stencil_b200.h $(wildcard include/stencil/*)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(ASTROFLAGS) -Iinclude -c $< -o $@
+bin/astaroth_b200: build/drv/astro_astaroth.o build/drv/astro_astaroth_utils.o build/drv/astro_b200_kernels.o build/drv/astro_statistics.o $(LIBA)
+	@mkdir -p bin
+	$(NVCC) $(DRVLINK) -o $@ build/drv/astro_astaroth.o build/drv/astro_astaroth_utils.o build/drv/astro_b200_kernels.o build/drv/astro_statistics.o $(LIBA)
+
+drivers: $(patsubst %,bin/%,$(DRIVERS)) bin/test_cuda bin/test_cpu bin/exchange_uniform bin/astaroth bin/astaroth_b200 bin/test_exchange_multigpu
 
 oracle:
 	$(MAKE) -C oracle

@@ -134,6 +134,26 @@ int sb_jacobi3d(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t ac
  * (bin/jacobi3d.cu:324-342 launches stencil_kernel once per slab).  lo/hi are n*3 int64. */
 int sb_jacobi3d_regions(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], int n,
                         const int64_t *lo, const int64_t *hi, const int64_t clo[3], const int64_t chi[3], void *stream);
+/* ---------------------------------------------------------------------------------------------
+ * Astaroth MHD substep: replaces `integrate_substep` + `solve<step>` of the reference's astaroth extract
+ * (astaroth/kernels.cu:62-87, astaroth/user_kernels.h:437-469, astaroth/integration.cuh:14-52).
+ * in / out: the VertexBufferArray (astaroth/kernels.h:22-27): 8 device arrays each, order lnrho, uux, uuy, uuz,
+ * ax, ay, az, entropy (astaroth/user_defines.h:112-120), all of raw size raw[3] = (mx, my, mz) elements, x fastest,
+ * including the radius-3 ghost cells.  [lo, hi): box to update in the reference's memory-offset coordinates
+ * (what the driver passes as Rect3 cr, astaroth/astaroth.cu:563-566); every cell needs 3 allocated cells around it.
+ * step 0..2 = Williamson RK3 substep; step 0 ignores the previous contents of `out`.
+ * params: the uniforms solve<> reads through DCONST (acDeviceLoadMeshInfo / acDeviceLoadScalarUniform,
+ * astaroth/kernels.cu:89-163).  variant: 0 auto, 1 cell kernel, 2 tile kernel.
+ * dtype_size 8 = double (the reference's AcReal), 4 = float.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  double inv_dsx, inv_dsy, inv_dsz;
+  double dt;
+  double cs2_sound, gamma, cp_sound, lnrho0, lnT0;
+  double mu0, nu_visc, zeta, eta;
+} sb_astaroth_params;
+int sb_astaroth_substep(int step, const void *const in[8], void *const out[8], int dtype_size, const int64_t raw[3],
+                        const int64_t lo[3], const int64_t hi[3], const sb_astaroth_params *params, int variant, void *stream);
 /* init_kernel, bin/jacobi3d.cu:18-29: fill region with a constant */
 int sb_fill(sb_pitched dst, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3], const int64_t hi[3],
             double value, void *stream);

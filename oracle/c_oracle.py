@@ -33,10 +33,25 @@ class Copy(C.Structure):
     ]
 
 
+class AcParams(C.Structure):
+    """so_ac_params: the uniforms solve<> reads (astaroth/user_kernels.h:389-427)."""
+
+    _fields_ = [(n, C.c_double) for n in ("inv_dsx", "inv_dsy", "inv_dsz", "dt", "cs2_sound", "gamma", "cp_sound", "lnrho0", "lnT0", "mu0", "nu_visc", "zeta", "eta")]
+
+
+def astaroth_conf_params(dt: float = 1e-8) -> AcParams:
+    """The values the reference driver ends up with: astaroth/astaroth.conf:10-67 for what the file sets,
+    the *_DEFAULT_VALUE statics (astaroth/user_kernels.h:30-35, 329, 367) for what it leaves out (NaN-filled
+    config entries are skipped by acDeviceLoadScalarUniform, astaroth/kernels.cu:96-100), dt from
+    astaroth/astaroth.cu:578."""
+    ds = 0.04908738521
+    return AcParams(1.0 / ds, 1.0 / ds, 1.0 / ds, dt, 1.0, 0.5, 1.0, 1.3, 1.2, 1.4, 5e-3, 0.01, 5e-3)
+
+
 def build(force: bool = False) -> str:
     """Compile the C oracle with gcc (present in this image and on the GPU box)."""
-    src = os.path.join(_HERE, "stencil_oracle.c")
-    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src)
+    srcs = [os.path.join(_HERE, f) for f in ("stencil_oracle.c", "astaroth_oracle.c")]
+    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs)
     if force or stale:
         march = "x86-64-v3"
         try:
@@ -68,6 +83,10 @@ def lib() -> C.CDLL:
             getattr(L, "so_fill_" + suf).argtypes = [C.c_void_p, Vec, Vec, Vec, ct]
             getattr(L, "so_sqdiff_" + suf).argtypes = [C.c_void_p, C.c_void_p, Vec, Vec, Vec]
             getattr(L, "so_sqdiff_" + suf).restype = C.c_double
+            getattr(L, "so_astaroth_substep_" + suf).argtypes = [
+                C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int64, C.c_int64,
+                C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(AcParams),
+            ]  # fmt: skip
         _lib = L
     return _lib
 
@@ -131,3 +150,17 @@ def fill(dst: np.ndarray, pos, ext, v: float) -> None:
 
 def sqdiff(a: np.ndarray, b: np.ndarray, pos, ext) -> float:
     return getattr(lib(), "so_sqdiff_" + _suffix(a))(a.ctypes.data, b.ctypes.data, _raw(a), Vec.of(pos), Vec.of(ext))
+
+
+def astaroth_substep(step: int, fin, fout, lo, hi, params: "AcParams") -> None:
+    """solve<step> on the memory-offset box [lo, hi) (astaroth/kernels.cu:62-87).  fin / fout: 8 arrays
+    (lnrho, uux, uuy, uuz, ax, ay, az, entropy) of identical (mz, my, mx) shape and dtype; fout is updated in place."""
+    a0 = fin[0]
+    assert len(fin) == 8 and len(fout) == 8
+    for a in list(fin) + list(fout):
+        assert a.shape == a0.shape and a.dtype == a0.dtype and a.flags.c_contiguous
+    mz, my, mx = a0.shape
+    pin = (C.c_void_p * 8)(*[a.ctypes.data for a in fin])
+    pout = (C.c_void_p * 8)(*[a.ctypes.data for a in fout])
+    clo, chi = (C.c_int64 * 3)(*lo), (C.c_int64 * 3)(*hi)
+    getattr(lib(), "so_astaroth_substep_" + _suffix(a0))(step, pin, pout, mx, my, clo, chi, C.byref(params))

@@ -19,7 +19,7 @@ OBJ="$OUT/obj"
 mkdir -p "$OUT" "$OBJ"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 STAMP="$OUT/.built"
-if [ -f "$STAMP" ] && [ "$STAMP" -nt "$HERE/build_ref.sh" ] && [ "$STAMP" -nt "$HERE/ref_exchange_uniform.cu" ] && [ "$STAMP" -nt "$REPO/src/mpi_shim.cpp" ] && [ -z "${FORCE:-}" ]; then
+if [ -f "$STAMP" ] && [ "$STAMP" -nt "$HERE/build_ref.sh" ] && [ "$STAMP" -nt "$HERE/ref_exchange_uniform.cu" ] && [ "$STAMP" -nt "$HERE/ref_astaroth_solve.cu" ] && [ "$STAMP" -nt "$REPO/src/mpi_shim.cpp" ] && [ -z "${FORCE:-}" ]; then
   echo "oracle/_ref up to date"; exit 0
 fi
 DEFS="-DSTENCIL_USE_MPI=1 -DSTENCIL_USE_CUDA=1 -DSTENCIL_USE_CUDA_AWARE_MPI=1 -DSTENCIL_USE_CUDA_GRAPH=1 -DSTENCIL_SETUP_STATS=1 -DSTENCIL_OUTPUT_LEVEL=2 -DNDEBUG -DCATCH_CONFIG_NO_POSIX_SIGNALS"
@@ -58,6 +58,11 @@ done
 for p in "${pids[@]}"; do wait "$p"; done
 $NVCC $LINK -o "$OUT/ref_astaroth" "$OBJ/astro_astaroth.o" "$OBJ/astro_kernels.o" "$OBJ/astro_astaroth_utils.o" "$OBJ/astro_statistics.o" "${LIBOBJS[@]}" "$OBJ/mpi_shim.o"
 cp "$REF/astaroth/astaroth.conf" "$OUT/astaroth.conf"
+# golden-vector generator for solve<step>: the reference's kernels.cu driven on a small box (oracle/ref/ref_astaroth_solve.cu)
+if [ ! -f "$OBJ/ref_astaroth_solve.o" ] || [ "$HERE/ref_astaroth_solve.cu" -nt "$OBJ/ref_astaroth_solve.o" ]; then
+  $NVCC $AFLAGS -c "$HERE/ref_astaroth_solve.cu" -o "$OBJ/ref_astaroth_solve.o"
+fi
+$NVCC $LINK -o "$OUT/ref_astaroth_solve" "$OBJ/ref_astaroth_solve.o" "$OBJ/astro_kernels.o" "$OBJ/astro_astaroth_utils.o" "${LIBOBJS[@]}" "$OBJ/mpi_shim.o"
 
 # the reference's own test suites
 pids=(); TC=(); TH=()

@@ -1,0 +1,428 @@
+// Astaroth `solve<step>` for sm_100a.  See astaroth.cuh for the reference anchors.
+//
+// What the reference does (astaroth/user_kernels.h:437-469 with block (32,1,4), astaroth/kernels.cu:67): every thread
+// rebuilds value + gradient + full hessian of all 8 fields from global memory -- 8 x 55 neighbour loads per cell, 254
+// registers -- and relies on L1 for reuse.
+//
+// What this file does:
+//  * only the derivatives the equations consume (lnrho, entropy: no cross terms; each vector component: two of the
+//    three cross terms) -- 296 instead of 440 neighbour values per cell;
+//  * tile kernel: a CTA owns a TX x TY column of cells and marches in z.  The halo'd planes z-3..z+3 of all 8 fields
+//    live in a shared-memory ring (FP64: 8 fields x 8 slots x 22 x 20 doubles = 220 KiB of the SM's 227 KiB); plane
+//    z+4 streams in with cp.async while plane z is computed, one __syncthreads per plane.  Every neighbour value is an
+//    LDS with an immediate offset (ring slot bases are 7 registers), x-y reuse never leaves the SM, and HBM sees each
+//    input plane once per tile (+ halo overlap served by L2);
+//  * cell kernel for thin boxes (the 3-cell exterior slabs): one thread per cell, neighbours through the read-only path.
+// Roofline: 8 reads + 8 reads of `out` + 8 writes per cell = 24 x sizeof(T) bytes (16 x for step 0, which ignores the
+// previous state); with ~300 shared-memory loads and ~900 FP instructions per cell the FP64 kernel is shared-memory /
+// DFMA-issue bound before it is HBM bound -- numbers in profiles/README.md.
+#include "astaroth.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace sb {
+namespace {
+
+enum { LNRHO = 0, UUX, UUY, UUZ, AX, AY, AZ, ENTROPY };
+
+template <typename T> struct AcConst {
+  T ix, iy, iz, dt, cs2s, gam, cp, lnrho0, lnT0, mu0, nu, zeta, eta;
+};
+
+template <typename T> AcConst<T> make_const(const AcParams &p) {
+  AcConst<T> c;
+  c.ix = T(p.inv_dsx), c.iy = T(p.inv_dsy), c.iz = T(p.inv_dsz), c.dt = T(p.dt);
+  c.cs2s = T(p.cs2_sound), c.gam = T(p.gamma), c.cp = T(p.cp_sound), c.lnrho0 = T(p.lnrho0), c.lnT0 = T(p.lnT0);
+  c.mu0 = T(p.mu0), c.nu = T(p.nu_visc), c.zeta = T(p.zeta), c.eta = T(p.eta);
+  return c;
+}
+
+template <typename T> struct AcArgs {
+  const T *in[kAcFields];
+  T *out[kAcFields];
+  int mx, my;
+  long long mxy;
+  int lo[3], hi[3];
+  int zchunk;
+  AcConst<T> P;
+};
+
+// value, gradient and the second derivatives one field contributes
+template <typename T> struct Dv {
+  T v, gx, gy, gz, xx, yy, zz, xy, xz, yz;
+};
+
+__device__ __forceinline__ double ac_exp(double x) { return exp(x); }
+__device__ __forceinline__ float ac_exp(float x) { return expf(x); }
+
+// first / second / cross derivative, same association order as astaroth/user_kernels.h:36-75
+template <typename T> __device__ __forceinline__ T d1(T m3, T m2, T m1, T p1, T p2, T p3, T inv) {
+  const T c1 = T(3.0) / T(4.0), c2 = -T(3.0) / T(20.0), c3 = T(1.0) / T(60.0);
+  T r = c1 * (p1 - m1);
+  r += c2 * (p2 - m2);
+  r += c3 * (p3 - m3);
+  return r * inv;
+}
+template <typename T> __device__ __forceinline__ T d2(T c, T m3, T m2, T m1, T p1, T p2, T p3, T inv) {
+  const T c0 = -T(49.0) / T(18.0), c1 = T(3.0) / T(2.0), c2 = -T(3.0) / T(20.0), c3 = T(1.0) / T(90.0);
+  T r = c0 * c;
+  r += c1 * (p1 + m1);
+  r += c2 * (p2 + m2);
+  r += c3 * (p3 + m3);
+  return r * inv * inv;
+}
+// a: the (+,+) diagonal, b: the (+,-) diagonal; am_i = a[3-i], ap_i = a[3+i]
+template <typename T>
+__device__ __forceinline__ T dc(T am3, T am2, T am1, T ap1, T ap2, T ap3, T bm3, T bm2, T bm1, T bp1, T bp2, T bp3, T inva, T invb) {
+  const T fac = T(1.0) / T(720.0);
+  const T c1 = T(270.0) * fac, c2 = -T(27.0) * fac, c3 = T(2.0) * fac;
+  T r = c1 * (ap1 + am1 - bp1 - bm1);
+  r += c2 * (ap2 + am2 - bp2 - bm2);
+  r += c3 * (ap3 + am3 - bp3 - bm3);
+  return r * inva * invb;
+}
+
+// `at(dx, dy, dz)` returns the field value at that offset from the cell (offsets are compile-time after inlining).
+template <typename T, bool XY, bool XZ, bool YZ, typename At> __device__ __forceinline__ Dv<T> derive(At at, const AcConst<T> &P) {
+  Dv<T> d;
+  const T c = at(0, 0, 0);
+  d.v = c;
+  {
+    const T m3 = at(-3, 0, 0), m2 = at(-2, 0, 0), m1 = at(-1, 0, 0), p1 = at(1, 0, 0), p2 = at(2, 0, 0), p3 = at(3, 0, 0);
+    d.gx = d1(m3, m2, m1, p1, p2, p3, P.ix);
+    d.xx = d2(c, m3, m2, m1, p1, p2, p3, P.ix);
+  }
+  {
+    const T m3 = at(0, -3, 0), m2 = at(0, -2, 0), m1 = at(0, -1, 0), p1 = at(0, 1, 0), p2 = at(0, 2, 0), p3 = at(0, 3, 0);
+    d.gy = d1(m3, m2, m1, p1, p2, p3, P.iy);
+    d.yy = d2(c, m3, m2, m1, p1, p2, p3, P.iy);
+  }
+  {
+    const T m3 = at(0, 0, -3), m2 = at(0, 0, -2), m1 = at(0, 0, -1), p1 = at(0, 0, 1), p2 = at(0, 0, 2), p3 = at(0, 0, 3);
+    d.gz = d1(m3, m2, m1, p1, p2, p3, P.iz);
+    d.zz = d2(c, m3, m2, m1, p1, p2, p3, P.iz);
+  }
+  d.xy = d.xz = d.yz = T(0);
+  if (XY) // derxy, astaroth/user_kernels.h:96-111
+    d.xy = dc(at(-3, -3, 0), at(-2, -2, 0), at(-1, -1, 0), at(1, 1, 0), at(2, 2, 0), at(3, 3, 0), at(-3, 3, 0), at(-2, 2, 0), at(-1, 1, 0),
+              at(1, -1, 0), at(2, -2, 0), at(3, -3, 0), P.ix, P.iy);
+  if (XZ) // derxz, :112-127
+    d.xz = dc(at(-3, 0, -3), at(-2, 0, -2), at(-1, 0, -1), at(1, 0, 1), at(2, 0, 2), at(3, 0, 3), at(-3, 0, 3), at(-2, 0, 2), at(-1, 0, 1),
+              at(1, 0, -1), at(2, 0, -2), at(3, 0, -3), P.ix, P.iz);
+  if (YZ) // deryz, :148-163
+    d.yz = dc(at(0, -3, -3), at(0, -2, -2), at(0, -1, -1), at(0, 1, 1), at(0, 2, 2), at(0, 3, 3), at(0, -3, 3), at(0, -2, 2), at(0, -1, 1),
+              at(0, 1, -1), at(0, 2, -2), at(0, 3, -3), P.iy, P.iz);
+  return d;
+}
+
+template <int STEP, typename T> __device__ __forceinline__ T rk3(T prev, T curr, T roc, T dt) {
+  // Williamson (1980), astaroth/integration.cuh:14-37
+  const T alpha[4] = {0, T(.0), T(-5. / 9.), T(-153. / 128.)};
+  const T beta[4] = {0, T(1. / 3.), T(15. / 16.), T(8. / 15.)};
+  if (STEP == 0) return curr + beta[STEP + 1] * roc * dt;
+  return curr + beta[STEP + 1] * (alpha[STEP + 1] * (T(1.) / beta[STEP]) * (curr - prev) + roc * dt);
+}
+
+// continuity / momentum / induction / entropy (astaroth/user_kernels.h:376-428) + the RK3 update (:444-453).
+// `prev[f]` is the `out` field before the update (unused for STEP 0), `res[f]` what solve<> writes back.
+template <int STEP, typename T>
+__device__ __forceinline__ void physics(const Dv<T> &lr, const Dv<T> *u, const Dv<T> *a, const Dv<T> &s, const T *prev, T *res,
+                                        const AcConst<T> &P) {
+  const T ux = u[0].v, uy = u[1].v, uz = u[2].v;
+  const T divu = u[0].gx + u[1].gy + u[2].gz;
+  const T cont = -(ux * lr.gx + uy * lr.gy + uz * lr.gz) - divu;
+  // induction
+  const T Bx = a[2].gy - a[1].gz, By = a[0].gz - a[2].gx, Bz = a[1].gx - a[0].gy;
+  const T lax = a[0].xx + a[0].yy + a[0].zz, lay = a[1].xx + a[1].yy + a[1].zz, laz = a[2].xx + a[2].yy + a[2].zz;
+  const T indx = (uy * Bz - uz * By) + P.eta * lax;
+  const T indy = (uz * Bx - ux * Bz) + P.eta * lay;
+  const T indz = (ux * By - uy * Bx) + P.eta * laz;
+  // current density j = (grad div A - lap A) / mu0
+  const T imu0 = T(1.0) / P.mu0;
+  const T jx = imu0 * ((a[0].xx + a[1].xy + a[2].xz) - lax);
+  const T jy = imu0 * ((a[0].xy + a[1].yy + a[2].yz) - lay);
+  const T jz = imu0 * ((a[0].xz + a[1].yz + a[2].zz) - laz);
+  // momentum
+  const T S00 = (T(2.0) / T(3.0)) * u[0].gx - (T(1.0) / T(3.0)) * (u[1].gy + u[2].gz);
+  const T S01 = (T(1.0) / T(2.0)) * (u[0].gy + u[1].gx);
+  const T S02 = (T(1.0) / T(2.0)) * (u[0].gz + u[2].gx);
+  const T S11 = (T(2.0) / T(3.0)) * u[1].gy - (T(1.0) / T(3.0)) * (u[0].gx + u[2].gz);
+  const T S12 = (T(1.0) / T(2.0)) * (u[1].gz + u[2].gy);
+  const T S22 = (T(2.0) / T(3.0)) * u[2].gz - (T(1.0) / T(3.0)) * (u[0].gx + u[1].gy);
+  const T arg = P.gam * s.v / P.cp + (P.gam - T(1.0)) * (lr.v - P.lnrho0);
+  const T earg = ac_exp(arg);
+  const T cs2 = P.cs2s * earg;
+  const T rho = ac_exp(lr.v);
+  const T inv_rho = T(1.0) / rho;
+  const T icp = T(1.0) / P.cp;
+  const T gdx = u[0].xx + u[1].xy + u[2].xz, gdy = u[0].xy + u[1].yy + u[2].yz, gdz = u[0].xz + u[1].yz + u[2].zz;
+  const T lux = u[0].xx + u[0].yy + u[0].zz, luy = u[1].xx + u[1].yy + u[1].zz, luz = u[2].xx + u[2].yy + u[2].zz;
+  const T jxBx = jy * Bz - jz * By, jxBy = jz * Bx - jx * Bz, jxBz = jx * By - jy * Bx;
+  const T Sgx = S00 * lr.gx + S01 * lr.gy + S02 * lr.gz;
+  const T Sgy = S01 * lr.gx + S11 * lr.gy + S12 * lr.gz;
+  const T Sgz = S02 * lr.gx + S12 * lr.gy + S22 * lr.gz;
+  T momx = -(u[0].gx * ux + u[0].gy * uy + u[0].gz * uz);
+  T momy = -(u[1].gx * ux + u[1].gy * uy + u[1].gz * uz);
+  T momz = -(u[2].gx * ux + u[2].gy * uy + u[2].gz * uz);
+  momx = momx - cs2 * (icp * s.gx + lr.gx);
+  momy = momy - cs2 * (icp * s.gy + lr.gy);
+  momz = momz - cs2 * (icp * s.gz + lr.gz);
+  momx = momx + inv_rho * jxBx;
+  momy = momy + inv_rho * jxBy;
+  momz = momz + inv_rho * jxBz;
+  momx = momx + P.nu * ((lux + (T(1.0) / T(3.0)) * gdx) + T(2.0) * Sgx);
+  momy = momy + P.nu * ((luy + (T(1.0) / T(3.0)) * gdy) + T(2.0) * Sgy);
+  momz = momz + P.nu * ((luz + (T(1.0) / T(3.0)) * gdz) + T(2.0) * Sgz);
+  momx = momx + P.zeta * gdx;
+  momy = momy + P.zeta * gdy;
+  momz = momz + P.zeta * gdz;
+  // entropy.  exp(lnT) = exp(lnT0 + arg): the reference evaluates a third exp; exp(lnT0) * exp(arg) differs by rounding only
+  const T elnT = ac_exp(P.lnT0 + arg);
+  const T inv_pT = T(1.0) / (rho * elnT);
+  const T SS = (S00 * S00 + S01 * S01 + S02 * S02) + (S01 * S01 + S11 * S11 + S12 * S12) + (S02 * S02 + S12 * S12 + S22 * S22);
+  const T RHS = P.eta * P.mu0 * (jx * jx + jy * jy + jz * jz) + T(2.0) * rho * P.nu * SS + P.zeta * rho * divu * divu;
+  const T ls = s.xx + s.yy + s.zz, llr = lr.xx + lr.yy + lr.zz;
+  const T first = P.gam * icp * ls + (P.gam - T(1.0)) * llr;
+  const T s2x = P.gam * icp * s.gx + (P.gam - T(1.0)) * lr.gx;
+  const T s2y = P.gam * icp * s.gy + (P.gam - T(1.0)) * lr.gy;
+  const T s2z = P.gam * icp * s.gz + (P.gam - T(1.0)) * lr.gz;
+  const T t3x = P.gam * (icp * s.gx + lr.gx) + (-lr.gx);
+  const T t3y = P.gam * (icp * s.gy + lr.gy) + (-lr.gy);
+  const T t3z = P.gam * (icp * s.gz + lr.gz) + (-lr.gz);
+  const T chi = T(0.001) / (rho * P.cp);
+  const T heat = P.cp * chi * (first + (s2x * t3x + s2y * t3y + s2z * t3z));
+  const T ent = -(ux * s.gx + uy * s.gy + uz * s.gz) + inv_pT * RHS + heat;
+
+  res[LNRHO] = rk3<STEP>(prev[LNRHO], lr.v, cont, P.dt);
+  res[AX] = rk3<STEP>(prev[AX], a[0].v, indx, P.dt);
+  res[AY] = rk3<STEP>(prev[AY], a[1].v, indy, P.dt);
+  res[AZ] = rk3<STEP>(prev[AZ], a[2].v, indz, P.dt);
+  res[UUX] = rk3<STEP>(prev[UUX], ux, momx, P.dt);
+  res[UUY] = rk3<STEP>(prev[UUY], uy, momy, P.dt);
+  res[UUZ] = rk3<STEP>(prev[UUZ], uz, momz, P.dt);
+  res[ENTROPY] = rk3<STEP>(prev[ENTROPY], s.v, ent, P.dt);
+}
+
+template <int STEP, typename T, typename AtF>
+__device__ __forceinline__ void solve_cell(AtF atf, const AcArgs<T> &A, long long idx) {
+  // atf(f) returns the accessor of field f
+  Dv<T> u[3], a[3];
+  const Dv<T> lr = derive<T, false, false, false>(atf(LNRHO), A.P);
+  const Dv<T> s = derive<T, false, false, false>(atf(ENTROPY), A.P);
+  u[0] = derive<T, true, true, false>(atf(UUX), A.P);
+  u[1] = derive<T, true, false, true>(atf(UUY), A.P);
+  u[2] = derive<T, false, true, true>(atf(UUZ), A.P);
+  a[0] = derive<T, true, true, false>(atf(AX), A.P);
+  a[1] = derive<T, true, false, true>(atf(AY), A.P);
+  a[2] = derive<T, false, true, true>(atf(AZ), A.P);
+  T prev[kAcFields], res[kAcFields];
+#pragma unroll
+  for (int f = 0; f < kAcFields; ++f) prev[f] = (STEP == 0) ? T(0) : A.out[f][idx];
+  physics<STEP>(lr, u, a, s, prev, res, A.P);
+#pragma unroll
+  for (int f = 0; f < kAcFields; ++f) A.out[f][idx] = res[f];
+}
+
+// ---------------------------------------------------------------------------------------------- cell kernel
+// 128 threads shaped (1 << lgx, 1 << lgy, rest) so that thin boxes keep their lanes busy.
+template <int STEP, typename T> __global__ void __launch_bounds__(128) ac_cell_kernel(const __grid_constant__ AcArgs<T> A, int lgx, int lgy) {
+  const int t = threadIdx.x;
+  const int tx = t & ((1 << lgx) - 1), ty = (t >> lgx) & ((1 << lgy) - 1), tz = t >> (lgx + lgy);
+  const int x = A.lo[0] + (blockIdx.x << lgx) + tx;
+  const int y = A.lo[1] + (blockIdx.y << lgy) + ty;
+  const int z = A.lo[2] + blockIdx.z * (128 >> (lgx + lgy)) + tz;
+  if (x >= A.hi[0] || y >= A.hi[1] || z >= A.hi[2]) return;
+  const long long idx = (long long)z * A.mxy + (long long)y * A.mx + x;
+  const int mx = A.mx;
+  const long long mxy = A.mxy;
+  auto atf = [&](int f) {
+    const T *p = A.in[f] + idx;
+    return [p, mx, mxy](int dx, int dy, int dz) { return __ldg(p + dz * mxy + dy * mx + dx); };
+  };
+  solve_cell<STEP>(atf, A, idx);
+}
+
+// ---------------------------------------------------------------------------------------------- tile kernel
+template <int BYTES> __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int STEP, typename T, int TX, int TY, int NSLOT>
+__global__ void __launch_bounds__(TX *TY, 1) ac_tile_kernel(const __grid_constant__ AcArgs<T> A) {
+  constexpr int W = TX + 6, H = TY + 6, PL = W * H, NT = TX * TY, NL = (PL + NT - 1) / NT;
+  static_assert(NSLOT == 7 || NSLOT == 8, "ring of 7 (synchronous refill) or 8 (refill overlaps the computation) planes");
+  extern __shared__ __align__(16) unsigned char ac_smem[];
+  T *ring = reinterpret_cast<T *>(ac_smem); // [field][slot][H][W]
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int x0 = A.lo[0] + blockIdx.x * TX, y0 = A.lo[1] + blockIdx.y * TY;
+  const int z0 = A.lo[2] + blockIdx.z * A.zchunk;
+  const int z1 = min(z0 + A.zchunk, A.hi[2]);
+  const int mx = A.mx;
+  const long long mxy = A.mxy;
+
+  // what this thread fetches of every plane: element k of the halo'd tile -> (shared offset, global offset)
+  int goff[NL];
+#pragma unroll
+  for (int k = 0; k < NL; ++k) {
+    const int e = tid + k * NT;
+    const int r = e / W, c = e - r * W;
+    const int gx = min(x0 - 3 + c, mx - 1), gy = min(y0 - 3 + r, A.my - 1); // partial tiles: stay inside the allocation
+    goff[k] = (e < PL) ? gy * mx + gx : -1;
+  }
+  auto load_plane = [&](int p, int slot) {
+#pragma unroll
+    for (int f = 0; f < kAcFields; ++f) {
+      const T *src = A.in[f] + (long long)p * mxy;
+      T *dst = ring + (f * NSLOT + slot) * PL + tid;
+#pragma unroll
+      for (int k = 0; k < NL; ++k) {
+        if (goff[k] >= 0) cp_async<sizeof(T)>(dst + k * NT, src + goff[k]);
+      }
+    }
+  };
+
+  for (int p = z0 - 3; p <= z0 + 3; ++p) load_plane(p, p - z0 + 3);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+
+  const bool valid = (x0 + tx < A.hi[0]) && (y0 + ty < A.hi[1]);
+  const int o0 = (ty + 3) * W + tx + 3;
+  long long idx = (long long)z0 * mxy + (long long)(y0 + ty) * mx + (x0 + tx);
+
+  for (int z = z0; z < z1; ++z, idx += mxy) {
+    const int zi = z - z0;
+    const bool more = z + 1 < z1;
+    if (NSLOT == 8) {
+      if (more) load_plane(z + 4, (zi + 7) % NSLOT);
+      cp_async_commit();
+    }
+    if (valid) {
+      const T *b[7]; // plane z-3+k of field 0 at this thread's cell
+#pragma unroll
+      for (int k = 0; k < 7; ++k) b[k] = ring + ((zi + k) % NSLOT) * PL + o0;
+      auto atf = [&](int f) {
+        return [&b, f](int dx, int dy, int dz) { return b[dz + 3][f * NSLOT * PL + dy * W + dx]; };
+      };
+      solve_cell<STEP>(atf, A, idx);
+    }
+    if (NSLOT == 8) {
+      cp_async_wait_all();
+      __syncthreads();
+    } else {
+      __syncthreads(); // everyone is done with plane z-3 before its slot is refilled
+      if (more) {
+        load_plane(z + 4, (zi + 7) % NSLOT);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+      }
+    }
+  }
+}
+
+int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+template <int STEP, typename T, int TX, int TY, int NSLOT> int launch_tile(AcArgs<T> &A, cudaStream_t stream) {
+  constexpr size_t smem = size_t(kAcFields) * NSLOT * (TX + 6) * (TY + 6) * sizeof(T);
+  static unsigned long long configured = 0; // bit per device: the opt-in is per function and per context
+  auto kern = ac_tile_kernel<STEP, T, TX, TY, NSLOT>;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (!(configured >> (dev & 63) & 1)) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return -1;
+    configured |= 1ull << (dev & 63);
+  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ex = A.hi[0] - A.lo[0], ey = A.hi[1] - A.lo[1], ez = A.hi[2] - A.lo[2];
+  const int gx = (ex + TX - 1) / TX, gy = (ey + TY - 1) / TY;
+  // z chunks: a chunk of `len` planes costs len + 7 plane times (ring warm-up); one CTA per SM, so pick the chunk
+  // count that minimises (waves of CTAs) x (chunk cost) on this GPU
+  int best_len = ez;
+  long long best_cost = -1;
+  for (int n = 1; n <= ez && n <= 64; ++n) {
+    const int len = (ez + n - 1) / n;
+    const long long ctas = (long long)gx * gy * ((ez + len - 1) / len);
+    const long long cost = ((ctas + sms - 1) / sms) * (len + 7);
+    if (best_cost < 0 || cost < best_cost) best_cost = cost, best_len = len;
+  }
+  const int forced = env_int("SB_AC_ZCHUNK", 0);
+  A.zchunk = forced > 0 ? (forced < ez ? forced : ez) : best_len;
+  dim3 grid(gx, gy, (ez + A.zchunk - 1) / A.zchunk);
+  kern<<<grid, TX * TY, smem, stream>>>(A);
+  return 1;
+}
+
+template <int STEP, typename T> int launch_cell(AcArgs<T> &A, cudaStream_t stream) {
+  const int ex = A.hi[0] - A.lo[0], ey = A.hi[1] - A.lo[1], ez = A.hi[2] - A.lo[2];
+  int lgx = 0, lgy = 0;
+  while ((1 << lgx) < ex && lgx < 5) ++lgx; // up to 32 lanes along x
+  while ((1 << lgy) < ey && lgx + lgy < 7) ++lgy;
+  if ((1 << (lgx + lgy)) < 128 && ez == 1) { /* flat box: waste is unavoidable */ }
+  const int bz = 128 >> (lgx + lgy);
+  dim3 grid((ex + (1 << lgx) - 1) >> lgx, (ey + (1 << lgy) - 1) >> lgy, (ez + bz - 1) / bz);
+  ac_cell_kernel<STEP, T><<<grid, 128, 0, stream>>>(A, lgx, lgy);
+  return 1;
+}
+
+template <int STEP, typename T> int launch_step(AcArgs<T> &A, int variant, cudaStream_t stream) {
+  const int ex = A.hi[0] - A.lo[0], ey = A.hi[1] - A.lo[1], ez = A.hi[2] - A.lo[2];
+  if (variant == AC_AUTO) variant = (ex >= 8 && ey >= 8 && ez >= 8) ? AC_TILE : AC_CELL;
+  if (variant == AC_CELL) return launch_cell<STEP>(A, stream);
+  const int shape = env_int("SB_AC_SHAPE", 0);
+  if constexpr (sizeof(T) == 8) {
+    if (shape == 1) return launch_tile<STEP, T, 16, 16, 7>(A, stream);
+    return launch_tile<STEP, T, 16, 14, 8>(A, stream);
+  } else {
+    if (shape == 1) return launch_tile<STEP, T, 32, 8, 8>(A, stream);
+    return launch_tile<STEP, T, 32, 16, 8>(A, stream);
+  }
+}
+
+template <typename T>
+int launch_typed(int step, const AcFields &f, long long mx, long long my, const int lo[3], const int hi[3], const AcParams &p, int variant,
+                 cudaStream_t stream) {
+  AcArgs<T> A;
+  for (int i = 0; i < kAcFields; ++i) {
+    A.in[i] = static_cast<const T *>(f.in[i]);
+    A.out[i] = static_cast<T *>(f.out[i]);
+  }
+  A.mx = int(mx), A.my = int(my), A.mxy = mx * my;
+  for (int k = 0; k < 3; ++k) A.lo[k] = lo[k], A.hi[k] = hi[k];
+  A.zchunk = hi[2] - lo[2];
+  A.P = make_const<T>(p);
+  switch (step) {
+  case 0: return launch_step<0>(A, variant, stream);
+  case 1: return launch_step<1>(A, variant, stream);
+  case 2: return launch_step<2>(A, variant, stream);
+  default: return -1;
+  }
+}
+
+} // namespace
+
+int launch_astaroth_substep(int step, const AcFields &f, int dtype_size, long long mx, long long my, long long mz, const int lo[3],
+                            const int hi[3], const AcParams &p, int variant, cudaStream_t stream) {
+  for (int k = 0; k < 3; ++k) {
+    if (hi[k] <= lo[k]) return 0;
+  }
+  const long long m[3] = {mx, my, mz};
+  for (int k = 0; k < 3; ++k) {
+    if (lo[k] < 3 || hi[k] > m[k] - 3) return -2; // every cell needs three allocated neighbours on each side
+  }
+  if (mx * my >= (1ll << 31)) return -3; // in-plane offsets are 32-bit
+  if (dtype_size == 8) return launch_typed<double>(step, f, mx, my, lo, hi, p, variant, stream);
+  if (dtype_size == 4) return launch_typed<float>(step, f, mx, my, lo, hi, p, variant, stream);
+  return -1;
+}
+
+} // namespace sb

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "box_copy.cuh"
+#include "astaroth.cuh"
 #include "jacobi.cuh"
 
 #include "stencil/geometry.hpp"
@@ -757,6 +758,37 @@ int sb_jacobi3d(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t ac
   p.raw[1] = int(src.ysize);
   p.raw[2] = p.hi[2] + 1; // planes: the caller guarantees plane hi.z (one ghost plane above) exists
   const int n = sb::launch_jacobi(p, dtype_size, static_cast<cudaStream_t>(stream));
+  g_launches += uint64_t(n);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+int sb_astaroth_substep(int step, const void *const in[8], void *const out[8], int dtype_size, const int64_t raw[3], const int64_t lo[3],
+                        const int64_t hi[3], const sb_astaroth_params *params, int variant, void *stream) {
+  if (!in || !out || !raw || !lo || !hi || !params) return fail(SB_ERR_INVALID, "null argument");
+  if (step < 0 || step > 2) return fail(SB_ERR_INVALID, "substep %d (Williamson RK3 has substeps 0, 1, 2)", step);
+  if (dtype_size != 4 && dtype_size != 8) return fail(SB_ERR_INVALID, "dtype_size %d (4 = float, 8 = double)", dtype_size);
+  if (variant < 0 || variant > 2) return fail(SB_ERR_INVALID, "variant %d", variant);
+  sb::AcFields f;
+  for (int i = 0; i < sb::kAcFields; ++i) {
+    if (!in[i] || !out[i]) return fail(SB_ERR_INVALID, "field %d is null", i);
+    f.in[i] = in[i];
+    f.out[i] = out[i];
+  }
+  int ilo[3], ihi[3];
+  for (int k = 0; k < 3; ++k) {
+    if (raw[k] <= 0 || raw[k] >= (1ll << 31)) return fail(SB_ERR_INVALID, "raw size");
+    if (hi[k] > lo[k] && (lo[k] < 3 || hi[k] > raw[k] - 3))
+      return fail(SB_ERR_INVALID, "box [%lld,%lld) on axis %d needs 3 allocated cells on each side (raw %lld)", (long long)lo[k], (long long)hi[k], k,
+                  (long long)raw[k]);
+    ilo[k] = int(lo[k]);
+    ihi[k] = int(hi[k] > lo[k] ? hi[k] : lo[k]);
+  }
+  sb::AcParams p;
+  static_assert(sizeof(sb::AcParams) == sizeof(sb_astaroth_params), "same layout");
+  memcpy(&p, params, sizeof(p));
+  const int n = sb::launch_astaroth_substep(step, f, dtype_size, raw[0], raw[1], raw[2], ilo, ihi, p, variant, static_cast<cudaStream_t>(stream));
+  if (n < 0) return fail(SB_ERR_INVALID, "astaroth substep rejected (code %d)", n);
   g_launches += uint64_t(n);
   SB_CUDA(cudaGetLastError());
   return SB_OK;

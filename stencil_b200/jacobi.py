@@ -79,6 +79,8 @@ class Jacobi3D:
         self._devs = [d.gpu() for d in dd.domains()]
         self._multi_dev = len(set(self._devs)) > 1
         self._set_device = torch.cuda.set_device
+        self._ev_ext = None  # step_async: exterior-done events of the previous iteration (one per subdomain)
+        self._ev_int = None
         self.interior_cells = sum(int(np.prod([hi[a] - lo[a] for a in range(3)])) for lo, hi in interiors)
         self._parity0 = dd._parity
 
@@ -107,6 +109,8 @@ class Jacobi3D:
     def step(self) -> None:
         """One iteration, exactly the loop body of bin/jacobi3d.cu:296-368."""
         dd = self.dd
+        if self._ev_ext is not None:
+            self.synchronize()  # drain iterations queued by step_async
         if self.overlap:
             self.launch_interior()
             dd.exchange()
@@ -115,6 +119,71 @@ class Jacobi3D:
             dd.exchange()
             self.launch_whole()
         self.synchronize()
+        self._ev_ext = self._ev_int = None
+        dd.swap()
+
+    def step_async(self, timing=None) -> None:
+        """The same iteration with every dependency expressed as a CUDA event instead of a host-side stream
+        synchronisation, so consecutive iterations queue back to back on the device (the reference blocks the host
+        in exchange() and after the exterior kernels, bin/jacobi3d.cu:337-365).  Per subdomain, iteration i
+        (curr = A, next = B):
+
+            interior i   reads A, writes B interior      after exterior i-1 (wrote A's boundary, read B near it)
+            exchange i   reads A boundary, writes ghosts  after exterior i-1 of every sending subdomain
+            exterior i   reads A + ghosts, writes B rim   after exchange i, and after interior i-1 (read B's rim)
+
+        Remote ranks are ordered by the device-side ready/done flags of the exchange itself (dist.RemoteDomains):
+        `ready` is signalled on the exchange stream, i.e. after this rank's exterior i-1.  Results are bitwise
+        those of step().  `timing` = (event, event) recorded around subdomain 0's interior kernel."""
+        import torch
+
+        if not self.overlap:
+            raise RuntimeError("step_async needs the overlapped (interior/exterior) schedule")
+        dd = self.dd
+        nd = len(self._devs)
+        prev_ext, prev_int = self._ev_ext, self._ev_int
+        xs = dd.exchange_streams()
+        ev_int = []
+        for di, (dev, a) in enumerate(zip(self._devs, self._args())):
+            if self._multi_dev:
+                self._set_device(dev)
+            s = self.streams[di]
+            if prev_ext is not None:
+                s.wait_event(prev_ext[di])
+            if timing is not None and di == 0:
+                timing[0].record(s)
+            check(self._fn(*a[0]))
+            if timing is not None and di == 0:
+                timing[1].record(s)
+            e = torch.cuda.Event()
+            e.record(s)
+            ev_int.append(e)
+        if prev_ext is not None:
+            for x in xs:
+                for e in prev_ext:
+                    x.wait_event(e)
+        dd.exchange_async()
+        ev_x = []
+        for di, x in enumerate(xs):
+            if self._multi_dev:
+                self._set_device(self._devs[di])
+            e = torch.cuda.Event()
+            e.record(x)
+            ev_x.append(e)
+        ev_ext = []
+        for di, (dev, a) in enumerate(zip(self._devs, self._args())):
+            if self._multi_dev:
+                self._set_device(dev)
+            s = self.ext_streams[di]
+            for e in ev_x:
+                s.wait_event(e)
+            if prev_int is not None:
+                s.wait_event(prev_int[di])
+            check(self._fn_regions(*a[1]))
+            e = torch.cuda.Event()
+            e.record(s)
+            ev_ext.append(e)
+        self._ev_ext, self._ev_int = ev_ext, ev_int
         dd.swap()
 
     def synchronize(self) -> None:

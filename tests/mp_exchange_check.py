@@ -63,8 +63,12 @@ def main():
     dd.realize()
     jac = Jacobi3D(dd, h)
     jac.init(0.5)
-    for _ in range(5):
+    # two host-synchronised iterations, then three queued back to back (events + device-side flags only)
+    for _ in range(2):
         jac.step()
+    for _ in range(3):
+        jac.step_async()
+    jac.synchronize()
     ro = g.Radius.face_edge_corner(1, 0, 0)
     od = no.Domains((n, n, n), ro, [np.float64], n_subdomains=world)
     nxt = {}
