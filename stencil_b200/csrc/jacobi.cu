@@ -405,7 +405,8 @@ int launch_jacobi_regions(const JacobiParams &p, const JacobiRegions &r, int dty
   const long long total = r.first[r.n];
   if (r.n <= 0 || total <= 0) return 0;
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  static const int per_sm = env_int("SB_JACOBI_EXT_CTAS_PER_SM", 32);
+  if (blocks > 148ll * per_sm) blocks = 148ll * per_sm;
   if (dtype_size == 4)
     jacobi_regions_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(p, r);
   else

@@ -79,6 +79,10 @@ class Jacobi3D:
         self._devs = [d.gpu() for d in dd.domains()]
         self._multi_dev = len(set(self._devs)) > 1
         self._set_device = torch.cuda.set_device
+        import os
+
+        dbg = os.environ.get("SB_DEBUG_SKIP", "")
+        self._debug_skip = {"both": ("ext", "xchg")}.get(dbg, (dbg,) if dbg else ())
         self._ev_ext = None  # step_async: exterior-done events of the previous iteration (one per subdomain)
         self._ev_int = None
         self.interior_cells = sum(int(np.prod([hi[a] - lo[a] for a in range(3)])) for lo, hi in interiors)
@@ -140,6 +144,7 @@ class Jacobi3D:
         if not self.overlap:
             raise RuntimeError("step_async needs the overlapped (interior/exterior) schedule")
         dd = self.dd
+        skip = self._debug_skip  # timing diagnostics only (SB_DEBUG_SKIP=ext|xchg|both): results are wrong when set
         nd = len(self._devs)
         prev_ext, prev_int = self._ev_ext, self._ev_int
         xs = dd.exchange_streams()
@@ -162,7 +167,8 @@ class Jacobi3D:
             for x in xs:
                 for e in prev_ext:
                     x.wait_event(e)
-        dd.exchange_async()
+        if "xchg" not in skip:
+            dd.exchange_async()
         ev_x = []
         for di, x in enumerate(xs):
             if self._multi_dev:
@@ -179,7 +185,8 @@ class Jacobi3D:
                 s.wait_event(e)
             if prev_int is not None:
                 s.wait_event(prev_int[di])
-            check(self._fn_regions(*a[1]))
+            if "ext" not in skip:
+                check(self._fn_regions(*a[1]))
             e = torch.cuda.Event()
             e.record(s)
             ev_ext.append(e)
