@@ -39,6 +39,9 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-overlap", action="store_true")
+    p.add_argument("--schedule", default="fused", choices=["fused", "queued", "host-sync"],
+                   help="fused: one kernel per iteration = jacobi update + halo push into the neighbours' ghost cells (Jacobi3D.step_fused); "
+                   "queued: interior || exchange -> exterior with CUDA-event dependencies (step_async); host-sync: the reference's loop (step)")
     p.add_argument("--host-sync", action="store_true", help="block the host after the exchange and after the exterior kernels like bin/jacobi3d.cu:337-365 (default: iterations queue back to back, dependencies as CUDA events)")
     return p.parse_args()
 
@@ -254,9 +257,15 @@ def run_ours(args, rank, world):
             td.barrier()
             torch.cuda.synchronize()
 
-    queued = jac.overlap and not args.host_sync
+    schedule = "host-sync" if (args.host_sync or not jac.overlap) else args.schedule
+    if schedule == "fused" and os.environ.get("SB_FORCE_NCCL") == "1":
+        schedule = "queued"  # the fused schedule stores into peer memory
+    queued = schedule == "queued"
+    fused = schedule == "fused"
     for _ in range(max(args.warmup, 3)):
-        if queued:
+        if fused:
+            jac.step_fused()
+        elif queued:
             jac.step_async()
         else:
             jac.step()
@@ -276,6 +285,9 @@ def run_ours(args, rank, world):
     t_wall0 = time.perf_counter()
     ev_a.record(cs0)
     for i in range(args.steps):
+        if fused:
+            jac.step_fused(timing=(k0[i], k1[i]))
+            continue
         if queued:
             jac.step_async(timing=(k0[i], k1[i]))
             continue
@@ -295,6 +307,9 @@ def run_ours(args, rank, world):
         # the last iteration ends with the exterior kernels: bring them onto the timed stream
         for e in jac._ev_ext:
             cs0.wait_event(e)
+    if fused:
+        for e in jac._ev_fused:  # other subdomains of this process
+            cs0.wait_event(e)
     ev_b.record(cs0)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -312,7 +327,7 @@ def run_ours(args, rank, world):
 
     # ---- roofline of the dominant kernel (interior jacobi) ----------------------------------
     peak, peak_src = measured_peaks()
-    dom_cells = jac.interior_cells if jac.overlap else sum(int(np.prod(d.size())) for d in dd.domains())
+    dom_cells = jac.interior_cells if (jac.overlap and not fused) else sum(int(np.prod(d.size())) for d in dd.domains())
     if world == 1 and len(dd.domains()) > 1:
         # events sit on the first GPU's stream: attribute that subdomain's cells only
         dom_cells = dom_cells // len(dd.domains())
@@ -320,7 +335,7 @@ def run_ours(args, rank, world):
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm",
-        "kernel": "jacobi_march_kernel (interior region)" if jac.overlap else "jacobi_march_kernel (whole region)",
+        "kernel": "jacobi_march_kernel<PUSH> (whole region + halo push)" if fused else ("jacobi_march_kernel (interior region)" if jac.overlap else "jacobi_march_kernel (whole region)"),
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
@@ -409,7 +424,12 @@ def run_ours(args, rank, world):
                 "workload": f"jacobi3d {n}^3 per GPU radius-1 {args.dtype.upper()} (BASELINE configs[1]); global {X}x{Y}x{Z}",
                 "parallelism": f"{world} process(es) x {len(gpus)} GPU(s), 3-D domain decomposition, fused P2P halo write",
                 "overlap": jac.overlap,
-                "iteration_sync": "device-side (CUDA events + ready/done flags; Jacobi3D.step_async)" if queued else "host-side after exchange and exterior (Jacobi3D.step)",
+                "schedule": schedule,
+                "iteration_sync": {
+                    "fused": "one kernel per iteration: update + halo push into the neighbours' ghost cells; iterations ordered by CUDA events / device-side counters (Jacobi3D.step_fused)",
+                    "queued": "interior || exchange -> exterior, dependencies as CUDA events + ready/done flags (Jacobi3D.step_async)",
+                    "host-sync": "host-side after exchange and exterior (Jacobi3D.step, the reference's loop)",
+                }[schedule],
                 "l2": "inputs larger than L2 (2 x %.2f GiB per GPU vs 126 MB)" % (2 * es * (n + 2) ** 3 / 2**31),
                 "init": "0.5 everywhere, hot/cold spheres (bin/jacobi3d.cu:18-63)",
             },

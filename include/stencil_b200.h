@@ -154,6 +154,22 @@ typedef struct {
 } sb_astaroth_params;
 int sb_astaroth_substep(int step, const void *const in[8], void *const out[8], int dtype_size, const int64_t raw[3],
                         const int64_t lo[3], const int64_t hi[3], const sb_astaroth_params *params, int variant, void *stream);
+/* The jacobi step over the WHOLE compute region of a subdomain with the halo exchange of the NEXT iteration fused
+ * into it: every cell on a face of [lo, hi) is also stored into the ghost cell of the face neighbour that reads it
+ * next iteration.  Replaces, per iteration, the interior stencil_kernel launch + DistributedDomain::exchange()
+ * (src/stencil.cu:1002-1186: pack -> copy -> unpack of 6 face messages) + the <= 6 exterior launches of
+ * bin/jacobi3d.cu:296-368 by one kernel; results are bit-identical.  Face radius 1 only (bin/jacobi3d.cu:237-246).
+ * nbr[d], d = -x,+x,-y,+y,-z,+z: the neighbour's OUTPUT allocation of this iteration (its `next` buffer; may be this
+ * subdomain's own dst for a periodic self-neighbour, or a peer GPU's memory mapped by peer access / CUDA IPC);
+ * nbr_zsize[d]: planes of that allocation.  ptr == NULL: nothing is pushed in that direction.  The neighbour must
+ * have the same extent as this subdomain on the two axes orthogonal to d (always true for a grid partition).
+ * The caller orders iterations: this launch may start once every neighbour has finished the previous iteration. */
+typedef struct {
+  sb_pitched nbr[6];
+  int64_t nbr_zsize[6];
+} sb_halo_push;
+int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3],
+                      const int64_t hi[3], const int64_t clo[3], const int64_t chi[3], const sb_halo_push *push, void *stream);
 /* init_kernel, bin/jacobi3d.cu:18-29: fill region with a constant */
 int sb_fill(sb_pitched dst, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3], const int64_t hi[3],
             double value, void *stream);

@@ -44,6 +44,12 @@ class AstarothParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("inv_dsx", "inv_dsy", "inv_dsz", "dt", "cs2_sound", "gamma", "cp_sound", "lnrho0", "lnT0", "mu0", "nu_visc", "zeta", "eta")]
 
 
+class HaloPush(C.Structure):
+    """sb_halo_push: the six face neighbours' output allocations (-x, +x, -y, +y, -z, +z)."""
+
+    _fields_ = [("nbr", Pitched * 6), ("nbr_zsize", C.c_int64 * 6)]
+
+
 # every symbol include/stencil_b200.h declares: (restype, argtypes)
 _SIGS = {
     "sb_last_error": (C.c_char_p, []),
@@ -73,6 +79,7 @@ _SIGS = {
     "sb_jacobi3d": (C.c_int, [Pitched, Pitched, C.c_int, I3, I3, I3, I3, I3, C.c_void_p]),
     "sb_jacobi3d_regions": (C.c_int, [Pitched, Pitched, C.c_int, I3, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), I3, I3, C.c_void_p]),
     "sb_astaroth_substep": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, I3, I3, I3, C.POINTER(AstarothParams), C.c_int, C.c_void_p]),
+    "sb_jacobi3d_fused": (C.c_int, [Pitched, Pitched, C.c_int, I3, I3, I3, I3, I3, C.POINTER(HaloPush), C.c_void_p]),
     "sb_fill": (C.c_int, [Pitched, C.c_int, I3, I3, I3, C.c_double, C.c_void_p]),
     "sb_sqdiff": (C.c_int, [Pitched, Pitched, C.c_int, I3, I3, I3, C.c_void_p, C.c_void_p]),
     "sb_device_count": (C.c_int, [C.POINTER(C.c_int)]),

@@ -763,6 +763,45 @@ int sb_jacobi3d(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t ac
   return SB_OK;
 }
 
+int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3], const int64_t hi[3],
+                      const int64_t clo[3], const int64_t chi[3], const sb_halo_push *push, void *stream) {
+  if (!push) return fail(SB_ERR_INVALID, "null push table");
+  sb::JacobiParams p{};
+  int rc = to_alloc_box(src, dtype_size, acc_origin, lo, hi, p.lo, p.hi);
+  if (rc != SB_OK) return rc;
+  for (int k = 0; k < 3; ++k) {
+    if (p.hi[k] <= p.lo[k]) return SB_OK;
+    if (p.lo[k] < 1) return fail(SB_ERR_INVALID, "region needs one ghost cell below it on axis %d", k);
+  }
+  if (p.hi[0] - p.lo[0] < 16) return fail(SB_ERR_INVALID, "fused step needs at least 16 cells along x");
+  rc = jacobi_common(p, dst, src, dtype_size, acc_origin, clo, chi);
+  if (rc != SB_OK) return rc;
+  p.raw[2] = p.hi[2] + 1;
+  for (int d = 0; d < 6; ++d) {
+    const sb_pitched &n = push->nbr[d];
+    p.push_ptr[d] = nullptr;
+    if (!n.ptr) continue;
+    const long long npitch = n.pitch, nslice = n.pitch * n.ysize;
+    const long long nraw[3] = {npitch / dtype_size, (long long)n.ysize, (long long)push->nbr_zsize[d]};
+    const int axis = d / 2;
+    // -axis neighbour: my first cells are its HIGH ghost (index raw-1); +axis neighbour: my last cells are its ghost 0
+    const long long fixed = (d % 2 == 0) ? nraw[axis] - 1 : 0;
+    if (nraw[axis] < 3) return fail(SB_ERR_INVALID, "neighbour %d allocation too small", d);
+    const long long stride[3] = {(long long)dtype_size, npitch, nslice};
+    p.push_ptr[d] = static_cast<char *>(n.ptr) + fixed * stride[axis];
+    p.push_pitch[d] = npitch;
+    p.push_slice[d] = nslice;
+    // the two varying coordinates are MY allocation coordinates: they must exist in the neighbour's allocation
+    for (int k = 0; k < 3; ++k) {
+      if (k != axis && p.hi[k] > nraw[k]) return fail(SB_ERR_INVALID, "neighbour %d is smaller than this subdomain on axis %d", d, k);
+    }
+  }
+  const int n = sb::launch_jacobi_push(p, dtype_size, static_cast<cudaStream_t>(stream));
+  g_launches += uint64_t(n);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
 int sb_astaroth_substep(int step, const void *const in[8], void *const out[8], int dtype_size, const int64_t raw[3], const int64_t lo[3],
                         const int64_t hi[3], const sb_astaroth_params *params, int variant, void *stream) {
   if (!in || !out || !raw || !lo || !hi || !params) return fail(SB_ERR_INVALID, "null argument");

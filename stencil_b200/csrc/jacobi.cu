@@ -67,10 +67,16 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // starts its strip VX/2 cells earlier on the odd-phase rows, so the HBM-facing accesses (centre
 // loads, stores) stay full 128-bit vectors on every row; only the two L1-resident neighbour rows
 // (y-1, y+1), which have the opposite phase, are fetched as two half vectors.
-template <typename T, int VX, int RY, int MB, bool SHIFT>
+//
+// PUSH variant (RY = 1): the region is the whole compute region of the subdomain and every boundary cell is stored a
+// second time -- into the ghost cell of the face neighbour that will read it next iteration (own memory for a
+// periodic self-neighbour, a peer GPU's memory over NVLink otherwise).  The halo exchange of the next iteration is
+// thereby part of this kernel: no pack / unpack pass over the 8-byte-wide x faces, no separate exterior kernel.
+template <typename T, int VX, int RY, int MB, bool SHIFT, bool PUSH = false>
 __global__ void __launch_bounds__(256, MB)
     jacobi_march_kernel(const __grid_constant__ JacobiParams p, int tiles_x, int tiles_y) {
   static_assert(!SHIFT || (RY == 1 && VX >= 2), "the phase-shifted variant handles one row per warp");
+  static_assert(!PUSH || RY == 1, "the push variant handles one row per warp");
   using V = Vec<T, VX>;
   constexpr int WY = 8; // warps stacked in y
   const int lane = threadIdx.x & 31;
@@ -134,6 +140,9 @@ __global__ void __launch_bounds__(256, MB)
     dy2[j] = dyv * dyv;
   }
   const int gx0 = x + p.org[0];
+  // PUSH: is this warp's row a y face, does this lane hold an x-face cell?
+  const bool y_first = PUSH && (y == p.lo[1]), y_last = PUSH && (y == p.hi[1] - 1);
+  const bool x_face = PUSH && ((p.lo[0] >= x && p.lo[0] < x + VX) || (p.hi[0] - 1 >= x && p.hi[0] - 1 < x + VX));
 
   V A[RY], B[RY], C[RY];
 #pragma unroll
@@ -206,6 +215,24 @@ __global__ void __launch_bounds__(256, MB)
 #pragma unroll
           for (int i = 0; i < VX; ++i)
             if (cell_ok & (1u << i)) reinterpret_cast<T *>(pw[j])[i] = out.v[i];
+        }
+      }
+      if (PUSH) {
+        const bool z_first = (z == p.lo[2]), z_last = (z == p.hi[2] - 1);
+        if ((z_first | z_last | y_first | y_last | x_face) && row_ok[j]) { // rare: a face of the subdomain
+          const long long yy = y + j;
+#pragma unroll
+          for (int i = 0; i < VX; ++i) {
+            if (!(cell_ok & (1u << i))) continue;
+            const long long xb = (long long)(x + i) * (long long)sizeof(T);
+            const T v = out.v[i];
+            if (x + i == p.lo[0] && p.push_ptr[0]) *reinterpret_cast<T *>(p.push_ptr[0] + (long long)z * p.push_slice[0] + yy * p.push_pitch[0]) = v;
+            if (x + i == p.hi[0] - 1 && p.push_ptr[1]) *reinterpret_cast<T *>(p.push_ptr[1] + (long long)z * p.push_slice[1] + yy * p.push_pitch[1]) = v;
+            if (y_first && p.push_ptr[2]) *reinterpret_cast<T *>(p.push_ptr[2] + (long long)z * p.push_slice[2] + xb) = v;
+            if (y_last && p.push_ptr[3]) *reinterpret_cast<T *>(p.push_ptr[3] + (long long)z * p.push_slice[3] + xb) = v;
+            if (z_first && p.push_ptr[4]) *reinterpret_cast<T *>(p.push_ptr[4] + yy * p.push_pitch[4] + xb) = v;
+            if (z_last && p.push_ptr[5]) *reinterpret_cast<T *>(p.push_ptr[5] + yy * p.push_pitch[5] + xb) = v;
+          }
         }
       }
       pc[j] += S;
@@ -351,6 +378,17 @@ __global__ void __launch_bounds__(256) sqdiff_kernel(const char *a, const char *
   }
 }
 
+template <typename T, int VX, bool SHIFT> int launch_march_push(const JacobiParams &p, cudaStream_t stream) {
+  const int x0a = (p.lo[0] / VX) * VX;
+  const int tiles_x = (p.hi[0] - x0a + (SHIFT ? VX / 2 : 0) + 32 * VX - 1) / (32 * VX);
+  const int ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
+  const int tiles_z = (nz + p.zchunk - 1) / p.zchunk;
+  const int tiles_y = (ny + 7) / 8;
+  const long long blocks = (long long)tiles_x * tiles_y * tiles_z;
+  jacobi_march_kernel<T, VX, 1, 4, SHIFT, true><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
+  return 1;
+}
+
 template <typename T, int VX, bool SHIFT> int launch_march(const JacobiParams &p, int ry, int mb, cudaStream_t stream) {
   const int x0a = (p.lo[0] / VX) * VX;
   // a shifted row starts VX/2 cells early, so the last tile must reach VX/2 cells further
@@ -459,6 +497,30 @@ int launch_jacobi(const JacobiParams &p_in, int dtype_size, cudaStream_t stream)
   if (half_phase) return launch_march<float, 4, true>(p, ry, mb, stream);
   if (a % 8 == 0) return launch_march<float, 2, false>(p, ry, mb, stream);
   return launch_march<float, 1, false>(p, ry, mb, stream);
+}
+
+int launch_jacobi_push(const JacobiParams &p_in, int dtype_size, cudaStream_t stream) {
+  JacobiParams p = p_in;
+  const int ex = p.hi[0] - p.lo[0], ey = p.hi[1] - p.lo[1], ez = p.hi[2] - p.lo[2];
+  if (ex <= 0 || ey <= 0 || ez <= 0) return 0;
+  static const int zchunk_env = env_int("SB_JACOBI_ZCHUNK", 0);
+  static const int pf = env_int("SB_JACOBI_PREFETCH", 2);
+  static const int allow_shift = env_int("SB_JACOBI_SHIFT", 1);
+  p.zchunk = zchunk_env > 0 ? zchunk_env : 32;
+  if (p.zchunk > ez) p.zchunk = ez;
+  p.prefetch = pf;
+  const unsigned long long base = (unsigned long long)(uintptr_t)p.src | (unsigned long long)(uintptr_t)p.dst | (unsigned long long)p.slice;
+  const unsigned long long a = base | (unsigned long long)p.pitch;
+  const bool half_phase = allow_shift && (base % 16 == 0) && (p.pitch % 16 == 8);
+  if (dtype_size == 8) {
+    if (a % 16 == 0) return launch_march_push<double, 2, false>(p, stream);
+    if (half_phase) return launch_march_push<double, 2, true>(p, stream);
+    return launch_march_push<double, 1, false>(p, stream);
+  }
+  if (a % 16 == 0) return launch_march_push<float, 4, false>(p, stream);
+  if (half_phase) return launch_march_push<float, 4, true>(p, stream);
+  if (a % 8 == 0) return launch_march_push<float, 2, false>(p, stream);
+  return launch_march_push<float, 1, false>(p, stream);
 }
 
 int launch_fill(char *dst, long long pitch, long long slice, const int lo[3], const int hi[3], int dtype_size, double value,

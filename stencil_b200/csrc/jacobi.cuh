@@ -22,6 +22,13 @@ struct JacobiParams {
   int rad;       // sphere radius
   int zchunk;    // planes marched per CTA
   int prefetch;  // L2 prefetch distance in planes (0 = off)
+  // fused halo push (launch_jacobi_push): for direction d = -x,+x,-y,+y,-z,+z the address, inside the NEIGHBOUR's
+  // output allocation, of the ghost line/plane this subdomain's boundary cells belong to, already offset to the fixed
+  // coordinate of that face; the two varying coordinates are this subdomain's own allocation coordinates times the
+  // neighbour's pitch / slice.  nullptr = no push in that direction.
+  char *push_ptr[6];
+  long long push_pitch[6];
+  long long push_slice[6];
 };
 
 // Up to 8 thin regions (the exterior slabs of one subdomain) updated by ONE launch.
@@ -35,6 +42,9 @@ struct JacobiRegions {
 // returns the number of kernel launches issued (0 if the region is empty)
 int launch_jacobi_regions(const JacobiParams &p, const JacobiRegions &r, int dtype_size, cudaStream_t stream);
 int launch_jacobi(const JacobiParams &p, int dtype_size, cudaStream_t stream);
+// the same update over the WHOLE compute region [lo, hi) of a subdomain; every boundary cell is also stored into the
+// ghost cell of the face neighbour that needs it (p.push_*), so the next iteration needs no halo exchange
+int launch_jacobi_push(const JacobiParams &p, int dtype_size, cudaStream_t stream);
 int launch_fill(char *dst, long long pitch, long long slice, const int lo[3], const int hi[3], int dtype_size, double value,
                 cudaStream_t stream);
 int launch_sqdiff(const char *a, const char *b, long long pitch, long long slice, const int lo[3], const int hi[3],

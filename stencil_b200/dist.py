@@ -62,10 +62,10 @@ class RemoteDomains:
         self.dev = dd.domains_[0].gpu()
         self._opened: List[int] = []
         n = w.size
-        # my mailbox: ready[0..n) then done[0..n)
+        # my mailbox: ready[0..n), done[0..n), then step[0..n) (iteration counters of the fused jacobi schedule)
         p = C.c_void_p()
-        check(lib().sb_malloc(C.byref(p), 2 * n * 4, self.dev))
-        check(lib().sb_memset(p, 0, 2 * n * 4, self.dev, None))
+        check(lib().sb_malloc(C.byref(p), 3 * n * 4, self.dev))
+        check(lib().sb_memset(p, 0, 3 * n * 4, self.dev, None))
         check(lib().sb_device_sync(self.dev))
         self.flags = int(p.value)
 
@@ -129,6 +129,8 @@ class RemoteDomains:
         # local slots to poll, gathered contiguously is not possible (slots are indexed by rank), so wait per slot list
         self._ready_local = [self.flags + 4 * b for b in self.nbrs]
         self._done_local = [self.flags + 4 * (n + b) for b in self.nbrs]
+        self._step_remote = (C.c_void_p * max(k, 1))(*[self.peer_flags[b] + 4 * (2 * n + w.rank) for b in self.nbrs])
+        self._step_local = [self.flags + 4 * (2 * n + b) for b in self.nbrs]
 
     def pitched(self, idx: Vec, q: int, parity: int) -> Tuple[Pitched, int]:
         dom = self.remote[tuple(idx)]
@@ -173,6 +175,19 @@ class RemoteDomains:
                 s.wait_event(ev)
         check(lib().sb_signal(self._done_remote, len(self.nbrs), epoch, self.dev, stream_ptr(s)))
         self._wait_all(self._done_local, epoch, s)
+
+    def raw_of(self, idx: Vec) -> Vec:
+        return tuple(self.remote[tuple(idx)]["raw"])
+
+    def signal_step(self, value: int, stream) -> None:
+        """Tell every neighbour rank that this rank's iteration `value` has finished (stream-ordered)."""
+        if self.nbrs:
+            check(lib().sb_signal(self._step_remote, len(self.nbrs), value, self.dev, stream_ptr(stream)))
+
+    def wait_step(self, value: int, stream) -> None:
+        """Hold `stream` until every neighbour rank has finished iteration `value`."""
+        if self.nbrs:
+            self._wait_all(self._step_local, value, stream)
 
     def close(self) -> None:
         import torch.distributed as td

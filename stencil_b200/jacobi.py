@@ -13,7 +13,7 @@ from typing import List, Tuple
 
 import numpy as np
 
-from ._lib import check, i3, lib, stream_ptr
+from ._lib import HaloPush, Pitched, check, i3, lib, stream_ptr
 from .domain import DataHandle, DistributedDomain, Radius
 
 
@@ -83,6 +83,7 @@ class Jacobi3D:
 
         dbg = os.environ.get("SB_DEBUG_SKIP", "")
         self._debug_skip = {"both": ("ext", "xchg")}.get(dbg, (dbg,) if dbg else ())
+        self._ghosts_current = False  # step_fused: do the ghost cells of curr hold the neighbours' current values?
         self._ev_ext = None  # step_async: exterior-done events of the previous iteration (one per subdomain)
         self._ev_int = None
         self.interior_cells = sum(int(np.prod([hi[a] - lo[a] for a in range(3)])) for lo, hi in interiors)
@@ -113,8 +114,10 @@ class Jacobi3D:
     def step(self) -> None:
         """One iteration, exactly the loop body of bin/jacobi3d.cu:296-368."""
         dd = self.dd
-        if self._ev_ext is not None:
-            self.synchronize()  # drain iterations queued by step_async
+        self._ghosts_current = False
+        if self._ev_ext is not None or getattr(self, "_ev_fused", None) is not None:
+            self.synchronize()  # drain iterations queued by step_async / step_fused
+            self._ev_fused = None
         if self.overlap:
             self.launch_interior()
             dd.exchange()
@@ -144,6 +147,10 @@ class Jacobi3D:
         if not self.overlap:
             raise RuntimeError("step_async needs the overlapped (interior/exterior) schedule")
         dd = self.dd
+        self._ghosts_current = False
+        if getattr(self, "_ev_fused", None) is not None:
+            self.synchronize()
+            self._ev_fused = None
         skip = self._debug_skip  # timing diagnostics only (SB_DEBUG_SKIP=ext|xchg|both): results are wrong when set
         nd = len(self._devs)
         prev_ext, prev_int = self._ev_ext, self._ev_int
@@ -191,6 +198,113 @@ class Jacobi3D:
             e.record(s)
             ev_ext.append(e)
         self._ev_ext, self._ev_int = ev_ext, ev_int
+        dd.swap()
+
+    # ------------------------------------------------------------------ fused schedule
+    def _build_fused(self) -> None:
+        """Argument packs of sb_jacobi3d_fused per swap parity: the whole compute region + the six face neighbours'
+        output allocations (own memory, a peer GPU of this process, or another rank's IPC mapping)."""
+        from .domain import get_neighbor
+
+        dd, h = self.dd, self.h
+        r = dd.radius_
+        for d6 in ((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)):
+            if r.dir(d6) != 1:
+                raise RuntimeError("the fused jacobi schedule needs face radius 1 (bin/jacobi3d.cu:237-246)")
+        if getattr(dd, "_use_nccl", False):
+            raise RuntimeError("the fused jacobi schedule stores into peer memory: not available on the NCCL fallback")
+        dirs = ((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1))
+        self._fused_calls = []
+        self._fused_nbr_slots = []  # in-process neighbours of each local subdomain (stream dependencies)
+        for rel in (0, 1):
+            absolute = (self._parity0 + rel) & 1
+            per_dom = []
+            for di, d in enumerate(dd.domains()):
+                idx = tuple(dd.domain_idx_[di])
+                src = d.pitched(h.id, "curr" if rel == 0 else "next")
+                dst = d.pitched(h.id, "next" if rel == 0 else "curr")
+                push = HaloPush()
+                slots = set()
+                for k, dv in enumerate(dirs):
+                    nidx = get_neighbor(idx, dv, dd.partition_.dim)
+                    # the neighbour's NEXT buffer at this parity is its curr buffer of the other parity
+                    pn, _ = dd._pitched_of(nidx, h.id, absolute ^ 1)
+                    rank, slot = dd._owner[tuple(nidx)]
+                    if rank == dd._world.rank:
+                        raw = dd.domains_[slot].raw_size()
+                        slots.add(slot)
+                    else:
+                        raw = dd._remote.raw_of(nidx)
+                    push.nbr[k] = Pitched(pn.ptr, pn.pitch, pn.ysize)
+                    push.nbr_zsize[k] = raw[2]
+                creg = d.get_compute_region()
+                clo, chi = i3(self.creg[0]), i3(self.creg[1])
+                pack = (dst, src, d.elem_size(h.id), i3(d.accessor_origin()), i3(creg[0]), i3(creg[1]), clo, chi, push, stream_ptr(self.streams[di]))
+                per_dom.append(pack)
+                if rel == 0:
+                    self._fused_nbr_slots.append(sorted(slots))
+            self._fused_calls.append(per_dom)
+        self._fn_fused = lib().sb_jacobi3d_fused
+        self._fused_epoch = 0
+        self._ev_fused = None
+        self._ghosts_current = False
+
+    def step_fused(self, timing=None) -> None:
+        """One iteration as ONE kernel per subdomain: the jacobi update of the whole compute region, with every boundary
+        cell also stored into the ghost cell of the face neighbour that reads it next iteration (sb_jacobi3d_fused).
+        The halo exchange of bin/jacobi3d.cu:337 is thereby part of the previous iteration's kernel; what remains
+        between iterations is ordering -- CUDA events between the subdomains of this process, one device-side
+        counter per neighbour rank (dist.RemoteDomains.signal_step / wait_step).  Bitwise the results of step().
+        The first fused iteration after construction (or after step / step_async) runs a regular exchange()."""
+        import ctypes as C
+
+        import torch
+
+        if not hasattr(self, "_fused_calls"):
+            self._build_fused()
+        dd = self.dd
+        if self._ev_ext is not None:
+            self.synchronize()
+            self._ev_ext = self._ev_int = None
+        if not self._ghosts_current:
+            self.synchronize()
+            dd.exchange()  # ghost cells of curr, once; afterwards every iteration leaves them filled for the next
+            if dd._remote is not None:
+                import torch.distributed as td
+
+                td.barrier()  # every rank's exchange has landed before anybody's first fused kernel
+            self._ghosts_current = True
+            self._ev_fused = None
+        calls = self._fused_calls[(dd._parity - self._parity0) & 1]
+        prev = self._ev_fused
+        remote = dd._remote
+        events = []
+        for di, (dev, a) in enumerate(zip(self._devs, calls)):
+            if self._multi_dev:
+                self._set_device(dev)
+            s = self.streams[di]
+            if prev is not None:
+                for sj in self._fused_nbr_slots[di]:
+                    if sj != di:
+                        s.wait_event(prev[sj])
+            if remote is not None and self._fused_epoch > 0:
+                remote.wait_step(self._fused_epoch, s)
+            if timing is not None and di == 0:
+                timing[0].record(s)
+            check(self._fn_fused(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], C.byref(a[8]), a[9]))
+            if timing is not None and di == 0:
+                timing[1].record(s)
+            e = torch.cuda.Event()
+            e.record(s)
+            events.append(e)
+        self._fused_epoch += 1
+        if remote is not None:
+            # one counter per rank: signal after ALL local subdomains of this iteration are done
+            s0 = self.streams[0]
+            for e in events[1:]:
+                s0.wait_event(e)
+            remote.signal_step(self._fused_epoch, s0)
+        self._ev_fused = events
         dd.swap()
 
     def synchronize(self) -> None:

@@ -66,8 +66,12 @@ def main():
     # two host-synchronised iterations, then three queued back to back (events + device-side flags only)
     for _ in range(2):
         jac.step()
-    for _ in range(3):
-        jac.step_async()
+    fused = os.environ.get("SB_FORCE_NCCL") != "1"  # the fused schedule stores into peer memory
+    for it in range(3):
+        if fused and it != 1:
+            jac.step_fused()  # update + halo push into the neighbour ranks' ghost cells, ordered by device-side counters
+        else:
+            jac.step_async()
     jac.synchronize()
     ro = g.Radius.face_edge_corner(1, 0, 0)
     od = no.Domains((n, n, n), ro, [np.float64], n_subdomains=world)

@@ -203,7 +203,8 @@ def test_fused_exterior_launch_matches_per_slab_launches(dtype):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("ndom", [1, 2, 4])
 def test_step_async_is_bitwise_step(dtype, ndom):
-    """Jacobi3D.step_async (iterations queued back to back, dependencies as CUDA events) against Jacobi3D.step (host
+    """Jacobi3D.step_fused (whole region + halo push in one kernel) and
+    Jacobi3D.step_async (iterations queued back to back, dependencies as CUDA events) against Jacobi3D.step (host
     synchronisation after the exchange and after the exterior kernels, bin/jacobi3d.cu:337-365): identical fields
     after 25 iterations, also when the two are mixed.  With several GPUs the subdomains are spread over them."""
     import torch
@@ -214,7 +215,7 @@ def test_step_async_is_bitwise_step(dtype, ndom):
     ng = torch.cuda.device_count()
     gpus = [i % ng for i in range(ndom)]
     fields = []
-    for mode in ("sync", "async", "mixed"):
+    for mode in ("sync", "async", "mixed", "fused", "mixed_fused"):
         dd = sb.DistributedDomain(n, n, n)
         dd.set_gpus(gpus)
         dd.set_radius(jacobi_radius())
@@ -224,8 +225,10 @@ def test_step_async_is_bitwise_step(dtype, ndom):
             jac = Jacobi3D(dd, h)
             jac.init(0.5)
             for it in range(25):
-                if mode == "sync" or (mode == "mixed" and it % 7 == 3):
+                if mode == "sync" or (mode == "mixed" and it % 7 == 3) or (mode == "mixed_fused" and it % 9 == 4):
                     jac.step()
+                elif mode in ("fused", "mixed_fused") and not (mode == "mixed_fused" and it % 5 == 1):
+                    jac.step_fused()  # one kernel per subdomain: update + halo push into the neighbours' ghost cells
                 else:
                     jac.step_async()
             jac.synchronize()
