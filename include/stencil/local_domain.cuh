@@ -54,6 +54,10 @@ class LocalDomain {
 
   Dim3 low_ghost() const noexcept { return Dim3(radius_.x(-1), radius_.y(-1), radius_.z(-1)); }
 
+  // HBM layout rule: when every row of quantity i has the same 16-byte phase the allocation starts
+  // this many bytes into its cudaMalloc block, so that the first COMPUTE cell of every row is 16-byte aligned.
+  size_t lead_bytes(size_t i) const noexcept;
+
 public:
   LocalDomain(Dim3 sz, Dim3 origin, int dev);
   ~LocalDomain();

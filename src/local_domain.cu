@@ -4,6 +4,19 @@
 
 #include <nvToolsExt.h>
 
+#include <cstdlib>
+
+size_t LocalDomain::lead_bytes(size_t i) const noexcept {
+  static const bool enabled = [] {
+    const char *e = std::getenv("SB_ALLOC_ALIGN");
+    return !(e && e[0] == '0');
+  }();
+  const size_t es = dataElemSize_[i];
+  const size_t rowBytes = size_t(radius_.x(-1) + sz_.x + radius_.x(1)) * es;
+  if (!enabled || rowBytes % 16 != 0) return 0;
+  return (16 - (size_t(radius_.x(-1)) * es) % 16) % 16;
+}
+
 LocalDomain::LocalDomain(Dim3 sz, Dim3 origin, int dev)
     : sz_(sz), origin_(origin), radius_(Radius::constant(0)), devCurrDataPtrs_(nullptr), devNextDataPtrs_(nullptr),
       devDataElemSize_(nullptr), dev_(dev) {}
@@ -16,10 +29,10 @@ LocalDomain::~LocalDomain() {
   for (const auto &p : nextDataPtrs_) any = any || p.ptr;
   if (!any) return;
   CUDA_RUNTIME(cudaSetDevice(dev_));
-  for (const auto &p : currDataPtrs_)
-    if (p.ptr) CUDA_RUNTIME(cudaFree(p.ptr));
-  for (const auto &p : nextDataPtrs_)
-    if (p.ptr) CUDA_RUNTIME(cudaFree(p.ptr));
+  for (size_t i = 0; i < currDataPtrs_.size(); ++i) {
+    if (currDataPtrs_[i].ptr) CUDA_RUNTIME(cudaFree(static_cast<char *>(currDataPtrs_[i].ptr) - lead_bytes(i)));
+    if (nextDataPtrs_[i].ptr) CUDA_RUNTIME(cudaFree(static_cast<char *>(nextDataPtrs_[i].ptr) - lead_bytes(i)));
+  }
   if (devCurrDataPtrs_) CUDA_RUNTIME(cudaFree(devCurrDataPtrs_));
   if (devNextDataPtrs_) CUDA_RUNTIME(cudaFree(devNextDataPtrs_));
   if (devDataElemSize_) CUDA_RUNTIME(cudaFree(devDataElemSize_));
@@ -72,8 +85,9 @@ void LocalDomain::realize() {
     const size_t bytes = rowBytes * size_t(raw.y) * size_t(raw.z);
     for (std::vector<cudaPitchedPtr> *store : {&currDataPtrs_, &nextDataPtrs_}) {
       cudaPitchedPtr p{};
-      CUDA_RUNTIME(cudaMalloc(&p.ptr, bytes ? bytes : 1));
-      CUDA_RUNTIME(cudaMemset(p.ptr, 0, bytes));
+      CUDA_RUNTIME(cudaMalloc(&p.ptr, bytes + 32));
+      CUDA_RUNTIME(cudaMemset(p.ptr, 0, bytes + 32));
+      p.ptr = static_cast<char *>(p.ptr) + lead_bytes(size_t(i));
       p.pitch = rowBytes; // unpitched on purpose, see the header
       p.xsize = rowBytes;
       p.ysize = size_t(raw.y);

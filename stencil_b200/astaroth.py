@@ -41,9 +41,15 @@ def substep(step: int, fin: Sequence[int], fout: Sequence[int], dtype_size: int,
 class Astaroth:
     """Drives the 8-field RK3 iteration on a realized DistributedDomain whose first 8 quantities are FIELDS."""
 
-    def __init__(self, dd: DistributedDomain, handles: Sequence[DataHandle], params: Optional[AstarothParams] = None, overlap: bool = True,
-                 variant: int = AUTO):  # fmt: skip
+    def __init__(self, dd: DistributedDomain, handles: Sequence[DataHandle], params: Optional[AstarothParams] = None,
+                 overlap: Optional[bool] = None, variant: int = AUTO):  # fmt: skip
+        """overlap=None picks the faster schedule measured on B200 (profiles/README.md section 5): the FP64 tile kernel
+        fills every SM's shared memory, so a concurrent exchange only waits for it -- exchange first, then one launch
+        over the whole region; in FP32 the interior || exchange -> exterior split of the reference driver wins."""
         import torch
+
+        if overlap is None:
+            overlap = dd.domains()[0].elem_size(handles[0].id) == 4
 
         if len(handles) != 8:
             raise ValueError("astaroth needs the 8 fields " + ", ".join(FIELDS))

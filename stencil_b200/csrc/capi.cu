@@ -788,6 +788,8 @@ int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int6
     const long long fixed = (d % 2 == 0) ? nraw[axis] - 1 : 0;
     if (nraw[axis] < 3) return fail(SB_ERR_INVALID, "neighbour %d allocation too small", d);
     const long long stride[3] = {(long long)dtype_size, npitch, nslice};
+    if (axis == 0 && nslice != src.pitch * src.ysize)
+      return fail(SB_ERR_INVALID, "x neighbour %d must have this subdomain's plane size (fused x push advances both by one slice)", d);
     p.push_ptr[d] = static_cast<char *>(n.ptr) + fixed * stride[axis];
     p.push_pitch[d] = npitch;
     p.push_slice[d] = nslice;

@@ -70,8 +70,10 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 //
 // PUSH variant (RY = 1): the region is the whole compute region of the subdomain and every boundary cell is stored a
 // second time -- into the ghost cell of the face neighbour that will read it next iteration (own memory for a
-// periodic self-neighbour, a peer GPU's memory over NVLink otherwise).  The halo exchange of the next iteration is
-// thereby part of this kernel: no pack / unpack pass over the 8-byte-wide x faces, no separate exterior kernel.
+// periodic self-neighbour, a peer GPU's memory over NVLink otherwise): x faces inside the loop (one predicated branch
+// per step, taken by two lanes per row), y and z faces by an epilogue over the few warps that own them.
+// The halo exchange of the next iteration is thereby part of this kernel: no pack / unpack pass over the 8-byte-wide
+// x faces, no separate exterior kernel.
 template <typename T, int VX, int RY, int MB, bool SHIFT, bool PUSH = false>
 __global__ void __launch_bounds__(256, MB)
     jacobi_march_kernel(const __grid_constant__ JacobiParams p, int tiles_x, int tiles_y) {
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(256, MB)
   const int y = p.lo[1] + (by * WY + warp) * RY;         // first row of this warp
   // phase of this row inside a 16-byte vector, in elements (0 unless SHIFT)
   const int shift = SHIFT ? (int)((((unsigned long long)y * (unsigned long long)P) & (sizeof(T) * VX - 1)) / sizeof(T)) : 0;
-  const int x0w = (p.lo[0] / VX) * VX + bx * 32 * VX - shift; // first cell of this warp's strip (allocation index)
+  const int x0w = p.x0a + bx * 32 * VX - shift; // first cell of this warp's strip (allocation index)
   const int x = x0w + lane * VX;                              // first cell of this lane
   const int z0 = p.lo[2] + bz * p.zchunk;
   const int z1 = min(z0 + p.zchunk, p.hi[2]);
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(256, MB)
   // does this lane's vector lie inside the allocation row?  (SHIFT: a vector may hang over either end
   // of its row into the neighbouring row of the same allocation -- valid memory, masked cells)
   const bool xin = SHIFT ? true : (x + VX <= p.raw[0]);
-  const int xs = xin ? x : 0; // out-of-row lanes read (and discard) column 0
+  const int xs = xin ? x : (p.x0a >= 0 ? p.x0a : p.x0a + VX); // out-of-row lanes read (and discard) an aligned in-row vector
   const long long xoff = (long long)xs * (long long)sizeof(T);
 
   // row byte offsets inside a plane; rows beyond the allocation are clamped (their results are masked)
@@ -140,9 +142,23 @@ __global__ void __launch_bounds__(256, MB)
     dy2[j] = dyv * dyv;
   }
   const int gx0 = x + p.org[0];
-  // PUSH: is this warp's row a y face, does this lane hold an x-face cell?
-  const bool y_first = PUSH && (y == p.lo[1]), y_last = PUSH && (y == p.hi[1] - 1);
-  const bool x_face = PUSH && ((p.lo[0] >= x && p.lo[0] < x + VX) || (p.hi[0] - 1 >= x && p.hi[0] - 1 < x + VX));
+
+  // PUSH, x faces: the one lane of a row that holds the first (last) compute cell stores it a second time, into the
+  // ghost cell of the -x (+x) neighbour.  Both addresses advance by one slice per plane (the launcher checks that the
+  // neighbour's slice equals ours), so the loop carries nothing for it: `xdiff` is the constant distance between the two,
+  // and the marching loop pays one predicated branch per step.
+  long long xdiff = 0;
+  bool xpush = false;
+  if (PUSH && row_ok[0]) {
+#pragma unroll
+    for (int i = 0; i < VX; ++i) {
+      const int d = (x + i == p.lo[0]) ? 0 : ((x + i == p.hi[0] - 1) ? 1 : -1);
+      if (d >= 0 && p.push_ptr[d]) {
+        xdiff = (p.push_ptr[d] + (long long)z0 * p.push_slice[d] + (long long)y * p.push_pitch[d]) - pw[0];
+        xpush = true;
+      }
+    }
+  }
 
   V A[RY], B[RY], C[RY];
 #pragma unroll
@@ -218,21 +234,12 @@ __global__ void __launch_bounds__(256, MB)
         }
       }
       if (PUSH) {
-        const bool z_first = (z == p.lo[2]), z_last = (z == p.hi[2] - 1);
-        if ((z_first | z_last | y_first | y_last | x_face) && row_ok[j]) { // rare: a face of the subdomain
-          const long long yy = y + j;
+        if (xpush) { // two lanes per row
+          T v = out.v[0];
 #pragma unroll
-          for (int i = 0; i < VX; ++i) {
-            if (!(cell_ok & (1u << i))) continue;
-            const long long xb = (long long)(x + i) * (long long)sizeof(T);
-            const T v = out.v[i];
-            if (x + i == p.lo[0] && p.push_ptr[0]) *reinterpret_cast<T *>(p.push_ptr[0] + (long long)z * p.push_slice[0] + yy * p.push_pitch[0]) = v;
-            if (x + i == p.hi[0] - 1 && p.push_ptr[1]) *reinterpret_cast<T *>(p.push_ptr[1] + (long long)z * p.push_slice[1] + yy * p.push_pitch[1]) = v;
-            if (y_first && p.push_ptr[2]) *reinterpret_cast<T *>(p.push_ptr[2] + (long long)z * p.push_slice[2] + xb) = v;
-            if (y_last && p.push_ptr[3]) *reinterpret_cast<T *>(p.push_ptr[3] + (long long)z * p.push_slice[3] + xb) = v;
-            if (z_first && p.push_ptr[4]) *reinterpret_cast<T *>(p.push_ptr[4] + yy * p.push_pitch[4] + xb) = v;
-            if (z_last && p.push_ptr[5]) *reinterpret_cast<T *>(p.push_ptr[5] + yy * p.push_pitch[5] + xb) = v;
-          }
+          for (int i = 1; i < VX; ++i)
+            if (x + i == p.lo[0] || x + i == p.hi[0] - 1) v = out.v[i];
+          *reinterpret_cast<T *>(pw[j] + xdiff) = v;
         }
       }
       pc[j] += S;
@@ -250,6 +257,38 @@ __global__ void __launch_bounds__(256, MB)
     step(B, C, A);
     if (z >= z1) break;
     step(C, A, B);
+  }
+
+  if (PUSH) {
+    // y and z faces, after the loop: every lane re-reads the face cells IT stored in this chunk (its own writes: no
+    // barrier, L2-resident) and stores them into the ghost row / plane of the neighbour.  Only the two edge rows of the
+    // subdomain (2 of 512 warps-rows) and the first / last chunk take these paths.
+    if (!row_ok[0] || !cell_ok) return;
+    const char *mine = p.dst + (long long)y * P + (long long)x * (long long)sizeof(T);
+    const int dy = (y == p.lo[1]) ? 2 : ((y == p.hi[1] - 1) ? 3 : -1);
+    if (dy >= 0 && p.push_ptr[dy]) {
+      char *tgt = p.push_ptr[dy] + (long long)x * (long long)sizeof(T);
+#pragma unroll 8
+      for (int zz = z0; zz < z1; ++zz) {
+        const T *r = reinterpret_cast<const T *>(mine + (long long)zz * S);
+#pragma unroll
+        for (int i = 0; i < VX; ++i)
+          if (cell_ok & (1u << i)) reinterpret_cast<T *>(tgt + (long long)zz * p.push_slice[dy])[i] = r[i];
+      }
+    }
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const bool on = side == 0 ? (z0 == p.lo[2]) : (z1 == p.hi[2]);
+      char *tgt = p.push_ptr[4 + side];
+      if (!on || !tgt) continue;
+      const int zz = side == 0 ? z0 : z1 - 1;
+      const T *r = reinterpret_cast<const T *>(mine + (long long)zz * S);
+#pragma unroll
+      for (int i = 0; i < VX; ++i) {
+        if (cell_ok & (1u << i))
+          *reinterpret_cast<T *>(tgt + (long long)y * p.push_pitch[4 + side] + (long long)(x + i) * (long long)sizeof(T)) = r[i];
+      }
+    }
   }
 }
 
@@ -378,19 +417,25 @@ __global__ void __launch_bounds__(256) sqdiff_kernel(const char *a, const char *
   }
 }
 
+int env_int(const char *name, int dflt);
+
 template <typename T, int VX, bool SHIFT> int launch_march_push(const JacobiParams &p, cudaStream_t stream) {
-  const int x0a = (p.lo[0] / VX) * VX;
+  const int x0a = p.x0a;
   const int tiles_x = (p.hi[0] - x0a + (SHIFT ? VX / 2 : 0) + 32 * VX - 1) / (32 * VX);
   const int ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
   const int tiles_z = (nz + p.zchunk - 1) / p.zchunk;
   const int tiles_y = (ny + 7) / 8;
   const long long blocks = (long long)tiles_x * tiles_y * tiles_z;
-  jacobi_march_kernel<T, VX, 1, 4, SHIFT, true><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
+  static const int mb = env_int("SB_JACOBI_PUSH_MB", 4);
+  if (mb == 3)
+    jacobi_march_kernel<T, VX, 1, 3, SHIFT, true><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
+  else
+    jacobi_march_kernel<T, VX, 1, 4, SHIFT, true><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
   return 1;
 }
 
 template <typename T, int VX, bool SHIFT> int launch_march(const JacobiParams &p, int ry, int mb, cudaStream_t stream) {
-  const int x0a = (p.lo[0] / VX) * VX;
+  const int x0a = p.x0a;
   // a shifted row starts VX/2 cells early, so the last tile must reach VX/2 cells further
   const int tiles_x = (p.hi[0] - x0a + (SHIFT ? VX / 2 : 0) + 32 * VX - 1) / (32 * VX);
   const int ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
@@ -452,6 +497,8 @@ int launch_jacobi_regions(const JacobiParams &p, const JacobiRegions &r, int dty
   return 1;
 }
 
+static int pick_vectors(JacobiParams &p, int dtype_size, bool allow_shift, bool *shift);
+
 int launch_jacobi(const JacobiParams &p_in, int dtype_size, cudaStream_t stream) {
   JacobiParams p = p_in;
   const int ex = p.hi[0] - p.lo[0], ey = p.hi[1] - p.lo[1], ez = p.hi[2] - p.lo[2];
@@ -483,20 +530,44 @@ int launch_jacobi(const JacobiParams &p_in, int dtype_size, cudaStream_t stream)
   if (p.zchunk > ez) p.zchunk = ez;
   p.prefetch = pf;
 
-  const unsigned long long base = (unsigned long long)(uintptr_t)p.src | (unsigned long long)(uintptr_t)p.dst | (unsigned long long)p.slice;
-  const unsigned long long a = base | (unsigned long long)p.pitch;
   static const int allow_shift = env_int("SB_JACOBI_SHIFT", 1);
-  // rows whose pitch is a multiple of half a vector only: phase-shifted full vectors (see the kernel)
-  const bool half_phase = allow_shift && (base % 16 == 0) && (p.pitch % 16 == 8);
+  bool shift = false;
+  const int vx = pick_vectors(p, dtype_size, allow_shift != 0, &shift);
   if (dtype_size == 8) {
-    if (a % 16 == 0) return launch_march<double, 2, false>(p, ry, mb, stream);
-    if (half_phase) return launch_march<double, 2, true>(p, ry, mb, stream);
+    if (vx == 2) return shift ? launch_march<double, 2, true>(p, ry, mb, stream) : launch_march<double, 2, false>(p, ry, mb, stream);
     return launch_march<double, 1, false>(p, ry, mb, stream);
   }
-  if (a % 16 == 0) return launch_march<float, 4, false>(p, ry, mb, stream);
-  if (half_phase) return launch_march<float, 4, true>(p, ry, mb, stream);
-  if (a % 8 == 0) return launch_march<float, 2, false>(p, ry, mb, stream);
+  if (vx == 4) return shift ? launch_march<float, 4, true>(p, ry, mb, stream) : launch_march<float, 4, false>(p, ry, mb, stream);
+  if (vx == 2) return launch_march<float, 2, false>(p, ry, mb, stream);
   return launch_march<float, 1, false>(p, ry, mb, stream);
+}
+
+// Vector width and strip origin for a launch.  Rows whose pitch and slice are multiples of 16 bytes all have the phase
+// of the allocation base: LocalDomain places the base so that the first COMPUTE cell is 16-byte aligned (the whole
+// compute region of 512 cells is then exactly 8 strips of 32 lanes x 2 doubles); any other common phase of src and dst
+// works as well.  Returns VX (1 = scalar fallback) and sets p.x0a; `shift` reports the alternating-phase case.
+static int pick_vectors(JacobiParams &p, int dtype_size, bool allow_shift, bool *shift) {
+  const unsigned long long s = (unsigned long long)(uintptr_t)p.src, d = (unsigned long long)(uintptr_t)p.dst;
+  const int full = 16 / dtype_size;
+  *shift = false;
+  auto origin = [&](int vx, unsigned phase) {
+    const int xal = int(((16u - phase) & 15u) / unsigned(dtype_size)) % vx; // x (mod vx) of the aligned cells
+    int r = (p.lo[0] - xal) % vx;
+    if (r < 0) r += vx;
+    p.x0a = p.lo[0] - r;
+    return vx;
+  };
+  if (p.pitch % 16 == 0 && p.slice % 16 == 0 && (s & 15) == (d & 15) && (s & 15) % dtype_size == 0) {
+    // with a non-zero phase the first vector may start before x = 0: still inside the (256-byte aligned) allocation,
+    // whose first `phase` bytes are the lead pad
+    return origin(full, unsigned(s & 15));
+  }
+  if (allow_shift && (s & 15) == 0 && (d & 15) == 0 && p.slice % 16 == 0 && p.pitch % 16 == 8) {
+    *shift = true;
+    return origin(full, 0);
+  }
+  if (dtype_size == 4 && ((s | d | (unsigned long long)p.pitch | (unsigned long long)p.slice) % 8 == 0)) return origin(2, 0);
+  return origin(1, 0);
 }
 
 int launch_jacobi_push(const JacobiParams &p_in, int dtype_size, cudaStream_t stream) {
@@ -509,17 +580,14 @@ int launch_jacobi_push(const JacobiParams &p_in, int dtype_size, cudaStream_t st
   p.zchunk = zchunk_env > 0 ? zchunk_env : 32;
   if (p.zchunk > ez) p.zchunk = ez;
   p.prefetch = pf;
-  const unsigned long long base = (unsigned long long)(uintptr_t)p.src | (unsigned long long)(uintptr_t)p.dst | (unsigned long long)p.slice;
-  const unsigned long long a = base | (unsigned long long)p.pitch;
-  const bool half_phase = allow_shift && (base % 16 == 0) && (p.pitch % 16 == 8);
+  bool shift = false;
+  const int vx = pick_vectors(p, dtype_size, allow_shift != 0, &shift);
   if (dtype_size == 8) {
-    if (a % 16 == 0) return launch_march_push<double, 2, false>(p, stream);
-    if (half_phase) return launch_march_push<double, 2, true>(p, stream);
+    if (vx == 2) return shift ? launch_march_push<double, 2, true>(p, stream) : launch_march_push<double, 2, false>(p, stream);
     return launch_march_push<double, 1, false>(p, stream);
   }
-  if (a % 16 == 0) return launch_march_push<float, 4, false>(p, stream);
-  if (half_phase) return launch_march_push<float, 4, true>(p, stream);
-  if (a % 8 == 0) return launch_march_push<float, 2, false>(p, stream);
+  if (vx == 4) return shift ? launch_march_push<float, 4, true>(p, stream) : launch_march_push<float, 4, false>(p, stream);
+  if (vx == 2) return launch_march_push<float, 2, false>(p, stream);
   return launch_march_push<float, 1, false>(p, stream);
 }
 

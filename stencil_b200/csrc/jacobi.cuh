@@ -22,6 +22,7 @@ struct JacobiParams {
   int rad;       // sphere radius
   int zchunk;    // planes marched per CTA
   int prefetch;  // L2 prefetch distance in planes (0 = off)
+  int x0a;       // first cell of the first strip: the largest x <= lo[0] whose address is vector aligned (set by the launcher)
   // fused halo push (launch_jacobi_push): for direction d = -x,+x,-y,+y,-z,+z the address, inside the NEIGHBOUR's
   // output allocation, of the ghost line/plane this subdomain's boundary cells belong to, already offset to the fixed
   // coordinate of that face; the two varying coordinates are this subdomain's own allocation coordinates times the

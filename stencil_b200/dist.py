@@ -82,8 +82,9 @@ class RemoteDomains:
                 dd.domain_idx_[i]: {
                     "raw": d.raw_size(),
                     "elem_sizes": list(d.elem_sizes_),
-                    "curr": [export(p_) for p_ in d.curr_],
-                    "next": [export(p_) for p_ in d.next_],
+                    # (handle of the cudaMalloc block, offset of the allocation inside it): LocalDomain.lead_bytes
+                    "curr": [(export(d._base_of[p_]), p_ - d._base_of[p_]) for p_ in d.curr_],
+                    "next": [(export(d._base_of[p_]), p_ - d._base_of[p_]) for p_ in d.next_],
                 }
                 for i, d in enumerate(dd.domains_)
             },
@@ -111,8 +112,8 @@ class RemoteDomains:
                 self.remote[tuple(idx)] = {
                     "raw": tuple(dom["raw"]),
                     "elem_sizes": dom["elem_sizes"],
-                    "curr": [open_(h) for h in dom["curr"]],
-                    "next": [open_(h) for h in dom["next"]],
+                    "curr": [open_(h) + off for h, off in dom["curr"]],
+                    "next": [open_(h) + off for h, off in dom["next"]],
                 }
         # neighbour ranks: owners of any subdomain adjacent to one of mine (periodic, symmetric)
         from .domain import ALL_DIRS, get_neighbor

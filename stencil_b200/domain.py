@@ -224,22 +224,40 @@ class LocalDomain:
         self.names_.append(name)
         return DataHandle(len(self.dtypes_) - 1, dt, name)
 
+    def lead_bytes(self, es: int) -> int:
+        """HBM layout rule: when every row has the same 16-byte phase (pitch % 16 == 0) the
+        allocation starts `lead` bytes into its cudaMalloc block so that the first COMPUTE cell of every row is 16-byte
+        aligned -- 512 FP64 cells are then exactly 256 aligned vectors (8 warp strips) and the halo rows of the y / z
+        faces are 128-bit copyable.  The reference starts at the block (src/local_domain.cu:187-203); the layout inside
+        the allocation (x fastest, unpitched) is unchanged.  SB_ALLOC_ALIGN=0 restores the reference placement."""
+        import os
+
+        if os.environ.get("SB_ALLOC_ALIGN", "1") == "0":
+            return 0
+        raw = self.raw_size()
+        if (raw[0] * es) % 16 != 0:
+            return 0
+        return (16 - (self.radius_.x(-1) * es) % 16) % 16
+
     def realize(self) -> None:
         raw = self.raw_size()
+        self._base_of = {}  # pointer handed out -> cudaMalloc block (for free and CUDA IPC)
         for es in self.elem_sizes_:
             nbytes = raw[0] * raw[1] * raw[2] * es
+            lead = self.lead_bytes(es)
             for store in (self.curr_, self.next_):
                 p = C.c_void_p()
-                check(lib().sb_malloc(C.byref(p), nbytes, self.dev_))
-                check(lib().sb_memset(p, 0, nbytes, self.dev_, None))
-                store.append(int(p.value))
+                check(lib().sb_malloc(C.byref(p), nbytes + 32, self.dev_))
+                check(lib().sb_memset(p, 0, nbytes + 32, self.dev_, None))
+                store.append(int(p.value) + lead)
+                self._base_of[int(p.value) + lead] = int(p.value)
         check(lib().sb_device_sync(self.dev_))
         self._owned = True
 
     def free(self) -> None:
         if self._owned:
             for p in self.curr_ + self.next_:
-                lib().sb_free(C.c_void_p(p), self.dev_)
+                lib().sb_free(C.c_void_p(self._base_of.get(p, p)), self.dev_)
             self.curr_, self.next_, self._owned = [], [], False
 
     def __del__(self):

@@ -204,6 +204,8 @@ class Jacobi3D:
     def _build_fused(self) -> None:
         """Argument packs of sb_jacobi3d_fused per swap parity: the whole compute region + the six face neighbours'
         output allocations (own memory, a peer GPU of this process, or another rank's IPC mapping)."""
+        import os
+
         from .domain import get_neighbor
 
         dd, h = self.dd, self.h
@@ -237,6 +239,8 @@ class Jacobi3D:
                         raw = dd._remote.raw_of(nidx)
                     push.nbr[k] = Pitched(pn.ptr, pn.pitch, pn.ysize)
                     push.nbr_zsize[k] = raw[2]
+                    if os.environ.get("SB_DEBUG_NOPUSH"):  # timing diagnostics only: results are wrong
+                        push.nbr[k] = Pitched(None, 0, 0)
                 creg = d.get_compute_region()
                 clo, chi = i3(self.creg[0]), i3(self.creg[1])
                 pack = (dst, src, d.elem_size(h.id), i3(d.accessor_origin()), i3(creg[0]), i3(creg[1]), clo, chi, push, stream_ptr(self.streams[di]))
