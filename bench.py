@@ -308,7 +308,7 @@ def run_ours(args, rank, world):
         for e in jac._ev_ext:
             cs0.wait_event(e)
     if fused:
-        for e in jac._ev_fused:  # other subdomains of this process
+        for e in list(jac._ev_fused or ()) + list(getattr(jac, "_ev_fused_x", None) or ()):  # other subdomains, last x exchange
             cs0.wait_event(e)
     ev_b.record(cs0)
     barrier()
@@ -440,6 +440,7 @@ def run_ours(args, rank, world):
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    jac.close()
     dd.close()
 
 

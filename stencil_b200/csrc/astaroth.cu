@@ -8,7 +8,8 @@
 //  * only the derivatives the equations consume (lnrho, entropy: no cross terms; each vector component: two of the
 //    three cross terms) -- 296 instead of 440 neighbour values per cell;
 //  * tile kernel: a CTA owns a TX x TY column of cells and marches in z.  The halo'd planes z-3..z+3 of all 8 fields
-//    live in a shared-memory ring (FP64: 8 fields x 8 slots x 22 x 20 doubles = 220 KiB of the SM's 227 KiB); plane
+//    live in a shared-memory ring (FP64: 8 fields x 8 slots x 22 x 20 doubles = 220 KiB of the SM's 227 KiB; FP32: 32 x 8
+//    tiles, 133 KiB); plane
 //    z+4 streams in with cp.async while plane z is computed, one __syncthreads per plane.  Every neighbour value is an
 //    LDS with an immediate offset (ring slot bases are 7 registers), x-y reuse never leaves the SM, and HBM sees each
 //    input plane once per tile (+ halo overlap served by L2);
@@ -383,8 +384,9 @@ template <int STEP, typename T> int launch_step(AcArgs<T> &A, int variant, cudaS
     if (shape == 1) return launch_tile<STEP, T, 16, 16, 7>(A, stream);
     return launch_tile<STEP, T, 16, 14, 8>(A, stream);
   } else {
-    if (shape == 1) return launch_tile<STEP, T, 32, 8, 8>(A, stream);
-    return launch_tile<STEP, T, 32, 16, 8>(A, stream);
+    // measured on B200, 256^3 (profiles/README.md section 5): 32x8 tiles (256 threads) 1.12 ms, 32x16 (512 threads) 1.23 ms
+    if (shape == 1) return launch_tile<STEP, T, 32, 16, 8>(A, stream);
+    return launch_tile<STEP, T, 32, 8, 8>(A, stream);
   }
 }
 

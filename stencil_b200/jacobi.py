@@ -216,6 +216,15 @@ class Jacobi3D:
         if getattr(dd, "_use_nccl", False):
             raise RuntimeError("the fused jacobi schedule stores into peer memory: not available on the NCCL fallback")
         dirs = ((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1))
+        # An x face is one 8-byte cell per row.  Pushed cell by cell into another GPU it costs 17 us per iteration through
+        # in-process peer access (fine) but 78 us through CUDA-IPC mappings; collecting the column in a dense array and
+        # shipping it between kernels, or leaving it to the copy engine between kernels, costs 30-70 us of serialised
+        # small launches (all measured on 2 x B200, profiles/README.md section 6).  So when an x face crosses RANKS the
+        # queued schedule (x faces staged by the copy engine, hidden behind the interior kernel) is the faster one, and
+        # this schedule is not used.  One decision for the whole job: every rank evaluates the same partition.
+        part = dd.partition_
+        if any(dd._owner[tuple(i)][0] != dd._owner[tuple(get_neighbor(i, dv, part.dim))][0] for i in part.indices() for dv in dirs[:2]):
+            raise RuntimeError("x faces cross ranks: the queued schedule is faster than 8-byte stores through CUDA-IPC mappings")
         self._fused_calls = []
         self._fused_nbr_slots = []  # in-process neighbours of each local subdomain (stream dependencies)
         for rel in (0, 1):
@@ -265,7 +274,13 @@ class Jacobi3D:
         import torch
 
         if not hasattr(self, "_fused_calls"):
-            self._build_fused()
+            try:
+                self._build_fused()
+                self.fused_supported = all(d.size()[0] >= 16 for d in self.dd.domains())
+            except RuntimeError:
+                self._fused_calls, self.fused_supported = [], False
+        if not self.fused_supported:  # see _build_fused: the queued schedule computes the same iteration
+            return self.step_async(timing=timing)
         dd = self.dd
         if self._ev_ext is not None:
             self.synchronize()
@@ -310,6 +325,10 @@ class Jacobi3D:
             remote.signal_step(self._fused_epoch, s0)
         self._ev_fused = events
         dd.swap()
+
+    def close(self) -> None:
+        """Drain the queued work (everything else is owned by DistributedDomain.close())."""
+        self.synchronize()
 
     def synchronize(self) -> None:
         """Wait for the compute streams (bin/jacobi3d.cu:363-365)."""

@@ -55,7 +55,7 @@ def main():
     from oracle import c_oracle as co
     from oracle import geometry as g
 
-    n = 48
+    n = 128  # 64 cells along x per rank: whole warp strips, so the fused schedule ships dense x columns between ranks
     dd = sb.DistributedDomain(n, n, n)
     dd.set_gpus([local])
     dd.set_radius(jacobi_radius())

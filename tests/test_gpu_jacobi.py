@@ -211,7 +211,7 @@ def test_step_async_is_bitwise_step(dtype, ndom):
 
     from stencil_b200.jacobi import Jacobi3D, jacobi_radius
 
-    n = 96
+    n = 128  # 64 cells along x per subdomain when split: whole FP64 warp strips -> dense x staging between GPUs
     ng = torch.cuda.device_count()
     gpus = [i % ng for i in range(ndom)]
     fields = []
