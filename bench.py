@@ -152,9 +152,24 @@ class CpuJacobi:
         return self.cur if self.par == 0 else self.nxt
 
 
+def physical_cores() -> int:
+    try:
+        import psutil
+
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
 def time_cpu(n, dtype, steps, warmup, budget_s=None):
     from oracle import c_oracle as co
 
+    # all physical cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank; with one thread
+    # per hyperthread the OpenMP port measured 14x slower on the 64-core / 128-thread GPU boxes)
+    co.set_num_threads(physical_cores())
     cj = CpuJacobi(n, dtype)
     for _ in range(warmup):
         cj.step()
@@ -270,6 +285,9 @@ def run_ours(args, rank, world):
         else:
             jac.step()
     jac.synchronize()
+    if fused and not getattr(jac, "fused_supported", True):
+        # x faces cross ranks: Jacobi3D.step_fused delegates to the queued schedule (measured faster, see jacobi.py)
+        schedule, fused, queued = "queued", False, True
 
     # ---- device-resident timed region -------------------------------------------------------
     cs0 = jac.streams[0]
@@ -343,7 +361,10 @@ def run_ours(args, rank, world):
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes,
         "kernel_ms": kern_ms,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, from the committed `ncu --set full`
+        # captures (profiles/jacobi_fused_r1.summary.txt: 2.143 GB for the fused whole-region kernel, 0.998 x algorithmic;
+        # profiles/jacobi_march_r1.summary.txt: 2.118 GB for the interior kernel); not re-measured by this run
+        "traffic": (2143024000 if fused else 2118000000) if (n == 512 and args.dtype == "f64") else None,
         "step_frac_of_roofline": (2 * es * cells / ngpu) / (ms_step * 1e-3) / 1e9 / peak,
     }
 

@@ -798,6 +798,12 @@ int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int6
       if (k != axis && p.hi[k] > nraw[k]) return fail(SB_ERR_INVALID, "neighbour %d is smaller than this subdomain on axis %d", d, k);
     }
   }
+  // A periodic self-neighbour on both sides of an axis needs neither ghost cells nor a push: the kernel reads the
+  // opposite face of src in place (x: the edge lane's scalar, y: the row above / below a strip).  With alternating row
+  // phases (FP32 rows not a multiple of 16 bytes) the wrapped row must have the parity of the ghost row it replaces.
+  auto self = [&](int d) { return push->nbr[d].ptr == dst.ptr && push->nbr[d].pitch == dst.pitch && push->nbr[d].ysize == dst.ysize; };
+  if (self(0) && self(1)) p.xwrap = 1; // a request: launch_jacobi_push keeps the x pushes when the vector layout rules it out
+  if (self(2) && self(3) && (src.pitch % 16 == 0 || (p.hi[1] - p.lo[1]) % 2 == 0)) p.ywrap = 1, p.push_ptr[2] = p.push_ptr[3] = nullptr;
   const int n = sb::launch_jacobi_push(p, dtype_size, static_cast<cudaStream_t>(stream));
   g_launches += uint64_t(n);
   SB_CUDA(cudaGetLastError());

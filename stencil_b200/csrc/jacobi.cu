@@ -74,7 +74,7 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // per step, taken by two lanes per row), y and z faces by an epilogue over the few warps that own them.
 // The halo exchange of the next iteration is thereby part of this kernel: no pack / unpack pass over the 8-byte-wide
 // x faces, no separate exterior kernel.
-template <typename T, int VX, int RY, int MB, bool SHIFT, bool PUSH = false>
+template <typename T, int VX, int RY, int MB, bool SHIFT, int PUSH = 0> // PUSH: 0 plain, 1 fused halo push, 2 fused without x pushes
 __global__ void __launch_bounds__(256, MB)
     jacobi_march_kernel(const __grid_constant__ JacobiParams p, int tiles_x, int tiles_y) {
   static_assert(!SHIFT || (RY == 1 && VX >= 2), "the phase-shifted variant handles one row per warp");
@@ -113,15 +113,25 @@ __global__ void __launch_bounds__(256, MB)
   const char *ph[RY]; // edge scalar of each row, plane z
   char *pw[RY];       // output rows, plane z
   const bool edge_lane = (lane == 0) || (lane == 31);
-  const int hx = clampi(lane == 0 ? x - 1 : x + VX, 0, p.raw[0] - 1);
+  int hxv = lane == 0 ? x - 1 : x + VX;
+  if (PUSH && p.xwrap) { // periodic self-neighbour: the cell beyond a face is the first / last cell of the same row
+    if (hxv == p.lo[0] - 1) hxv = p.hi[0] - 1;
+    else if (hxv == p.hi[0]) hxv = p.lo[0];
+  }
+  const int hx = clampi(hxv, 0, p.raw[0] - 1);
 #pragma unroll
   for (int j = 0; j < RY; ++j) {
     pc[j] = src + (long long)(z0 + 1) * S + yo(y + j) + xoff;
     ph[j] = src + (long long)z0 * S + yo(y + j) + (long long)hx * (long long)sizeof(T);
     pw[j] = p.dst + (long long)z0 * S + (long long)(y + j) * P + (long long)x * (long long)sizeof(T);
   }
-  const char *pu = src + (long long)z0 * S + yo(y - 1) + xoff;  // row above the strip, plane z
-  const char *pd = src + (long long)z0 * S + yo(y + RY) + xoff; // row below the strip, plane z
+  int yu = y - 1, yd = y + RY;
+  if (PUSH && p.ywrap) { // periodic self-neighbour: the row beyond a face is the opposite face row
+    if (yu == p.lo[1] - 1) yu = p.hi[1] - 1;
+    if (yd == p.hi[1]) yd = p.lo[1];
+  }
+  const char *pu = src + (long long)z0 * S + yo(yu) + xoff; // row above the strip, plane z
+  const char *pd = src + (long long)z0 * S + yo(yd) + xoff; // row below the strip, plane z
 
   // store masks
   bool row_ok[RY];
@@ -149,7 +159,7 @@ __global__ void __launch_bounds__(256, MB)
   // and the marching loop pays one predicated branch per step.
   long long xdiff = 0;
   bool xpush = false;
-  if (PUSH && row_ok[0]) {
+  if (PUSH == 1 && row_ok[0]) {
 #pragma unroll
     for (int i = 0; i < VX; ++i) {
       const int d = (x + i == p.lo[0]) ? 0 : ((x + i == p.hi[0] - 1) ? 1 : -1);
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(256, MB)
             if (cell_ok & (1u << i)) reinterpret_cast<T *>(pw[j])[i] = out.v[i];
         }
       }
-      if (PUSH) {
+      if (PUSH == 1) {
         if (xpush) { // two lanes per row
           T v = out.v[0];
 #pragma unroll
@@ -426,11 +436,10 @@ template <typename T, int VX, bool SHIFT> int launch_march_push(const JacobiPara
   const int tiles_z = (nz + p.zchunk - 1) / p.zchunk;
   const int tiles_y = (ny + 7) / 8;
   const long long blocks = (long long)tiles_x * tiles_y * tiles_z;
-  static const int mb = env_int("SB_JACOBI_PUSH_MB", 4);
-  if (mb == 3)
-    jacobi_march_kernel<T, VX, 1, 3, SHIFT, true><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
-  else
-    jacobi_march_kernel<T, VX, 1, 4, SHIFT, true><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
+  if (p.push_ptr[0] || p.push_ptr[1])
+    jacobi_march_kernel<T, VX, 1, 4, SHIFT, 1><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
+  else // no x face to push (periodic self-neighbour read in place, or nothing asked): the loop is the plain kernel's
+    jacobi_march_kernel<T, VX, 1, 4, SHIFT, 2><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
   return 1;
 }
 
@@ -582,6 +591,11 @@ int launch_jacobi_push(const JacobiParams &p_in, int dtype_size, cudaStream_t st
   p.prefetch = pf;
   bool shift = false;
   const int vx = pick_vectors(p, dtype_size, allow_shift != 0, &shift);
+  // x wrap (periodic self-neighbour read in place) works through the edge lanes' scalar load, so the first compute cell
+  // must open lane 0 of the first strip and the last one must close lane 31 of the last strip; otherwise the ghost
+  // column is read by a vector load or a shuffle and the x faces are pushed into the ghost cells like any other face
+  if (p.xwrap && !(!shift && p.x0a == p.lo[0] && (p.hi[0] - p.lo[0]) % (32 * vx) == 0)) p.xwrap = 0;
+  if (p.xwrap) p.push_ptr[0] = p.push_ptr[1] = nullptr;
   if (dtype_size == 8) {
     if (vx == 2) return shift ? launch_march_push<double, 2, true>(p, stream) : launch_march_push<double, 2, false>(p, stream);
     return launch_march_push<double, 1, false>(p, stream);

@@ -30,6 +30,10 @@ struct JacobiParams {
   char *push_ptr[6];
   long long push_pitch[6];
   long long push_slice[6];
+  // periodic self-neighbour along x / y (fused launch only): the first / last column (row) takes its out-of-subdomain
+  // neighbour from the OPPOSITE face of src instead of from the ghost cells -- a pointer set up before the marching loop,
+  // so that axis needs no exchange and no push at all
+  int xwrap, ywrap;
 };
 
 // Up to 8 thin regions (the exterior slabs of one subdomain) updated by ONE launch.
