@@ -167,6 +167,15 @@ int sb_astaroth_substep(int step, const void *const in[8], void *const out[8], i
 typedef struct {
   sb_pitched nbr[6];
   int64_t nbr_zsize[6];
+  /* Dense x faces (x neighbour owned by another rank): if x_dense[s] != 0 (s = 0: -x side, 1: +x side), nbr[s].ptr is
+   * not a field allocation but a dense array in the NEIGHBOUR's memory, (rows x planes) elements indexed [y][z] (z
+   * fastest, like the march) in THIS subdomain's allocation coordinates; nbr[s].ysize = rows, nbr_zsize[s] = planes.
+   * The kernel stages the column in shared memory and writes 256-byte lines instead of one 8-byte store per row and
+   * plane.  x_recv[s], if not NULL, is such an array (this subdomain's rows x planes) received FROM the neighbour on
+   * side s: the out-of-subdomain x neighbour of the first / last column is read from it instead of from the ghost
+   * column of src.  Needs a 16-byte aligned first compute cell and whole warp strips along x. */
+  int64_t x_dense[2];
+  const void *x_recv[2];
 } sb_halo_push;
 int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3],
                       const int64_t hi[3], const int64_t clo[3], const int64_t chi[3], const sb_halo_push *push, void *stream);

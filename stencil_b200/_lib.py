@@ -47,7 +47,7 @@ class AstarothParams(C.Structure):
 class HaloPush(C.Structure):
     """sb_halo_push: the six face neighbours' output allocations (-x, +x, -y, +y, -z, +z)."""
 
-    _fields_ = [("nbr", Pitched * 6), ("nbr_zsize", C.c_int64 * 6)]
+    _fields_ = [("nbr", Pitched * 6), ("nbr_zsize", C.c_int64 * 6), ("x_dense", C.c_int64 * 2), ("x_recv", C.c_void_p * 2)]
 
 
 # every symbol include/stencil_b200.h declares: (restype, argtypes)

@@ -784,6 +784,14 @@ int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int6
     const long long npitch = n.pitch, nslice = n.pitch * n.ysize;
     const long long nraw[3] = {npitch / dtype_size, (long long)n.ysize, (long long)push->nbr_zsize[d]};
     const int axis = d / 2;
+    if (axis == 0 && push->x_dense[d]) { // dense [y][z] array in the neighbour's memory, my allocation coordinates
+      if (n.ysize < p.hi[1] || push->nbr_zsize[d] < p.hi[2]) return fail(SB_ERR_INVALID, "dense x array %d too small", d);
+      p.push_ptr[d] = static_cast<char *>(n.ptr);
+      p.push_pitch[d] = (long long)push->nbr_zsize[d] * dtype_size;
+      p.push_slice[d] = dtype_size;
+      p.xdense[d] = 1;
+      continue;
+    }
     // -axis neighbour: my first cells are its HIGH ghost (index raw-1); +axis neighbour: my last cells are its ghost 0
     const long long fixed = (d % 2 == 0) ? nraw[axis] - 1 : 0;
     if (nraw[axis] < 3) return fail(SB_ERR_INVALID, "neighbour %d allocation too small", d);
@@ -798,6 +806,10 @@ int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int6
       if (k != axis && p.hi[k] > nraw[k]) return fail(SB_ERR_INVALID, "neighbour %d is smaller than this subdomain on axis %d", d, k);
     }
   }
+  for (int sd = 0; sd < 2; ++sd) {
+    p.xghost_ptr[sd] = static_cast<const char *>(push->x_recv[sd]);
+    p.xghost_pitch[sd] = (long long)(p.hi[2] + 1) * dtype_size; // [y][z] over this subdomain's planes (raw z = hi.z + 1)
+  }
   // A periodic self-neighbour on both sides of an axis needs neither ghost cells nor a push: the kernel reads the
   // opposite face of src in place (x: the edge lane's scalar, y: the row above / below a strip).  With alternating row
   // phases (FP32 rows not a multiple of 16 bytes) the wrapped row must have the parity of the ghost row it replaces.
@@ -805,6 +817,7 @@ int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int6
   if (self(0) && self(1)) p.xwrap = 1; // a request: launch_jacobi_push keeps the x pushes when the vector layout rules it out
   if (self(2) && self(3) && (src.pitch % 16 == 0 || (p.hi[1] - p.lo[1]) % 2 == 0)) p.ywrap = 1, p.push_ptr[2] = p.push_ptr[3] = nullptr;
   const int n = sb::launch_jacobi_push(p, dtype_size, static_cast<cudaStream_t>(stream));
+  if (n < 0) return fail(SB_ERR_INVALID, "dense x faces need a 16-byte aligned first compute cell, whole warp strips along x and z chunks of <= 32 planes");
   g_launches += uint64_t(n);
   SB_CUDA(cudaGetLastError());
   return SB_OK;

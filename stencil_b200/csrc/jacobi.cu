@@ -74,7 +74,7 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // per step, taken by two lanes per row), y and z faces by an epilogue over the few warps that own them.
 // The halo exchange of the next iteration is thereby part of this kernel: no pack / unpack pass over the 8-byte-wide
 // x faces, no separate exterior kernel.
-template <typename T, int VX, int RY, int MB, bool SHIFT, int PUSH = 0> // PUSH: 0 plain, 1 fused halo push, 2 fused without x pushes
+template <typename T, int VX, int RY, int MB, bool SHIFT, int PUSH = 0> // PUSH: 0 plain, 1 fused halo push, 2 fused without x pushes, 3 fused with dense x faces
 __global__ void __launch_bounds__(256, MB)
     jacobi_march_kernel(const __grid_constant__ JacobiParams p, int tiles_x, int tiles_y) {
   static_assert(!SHIFT || (RY == 1 && VX >= 2), "the phase-shifted variant handles one row per warp");
@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256, MB)
   const char *ph[RY]; // edge scalar of each row, plane z
   char *pw[RY];       // output rows, plane z
   const bool edge_lane = (lane == 0) || (lane == 31);
+  long long phstep = S; // per-plane advance of ph (mode 3: a dense x-ghost array is z fastest)
   int hxv = lane == 0 ? x - 1 : x + VX;
   if (PUSH && p.xwrap) { // periodic self-neighbour: the cell beyond a face is the first / last cell of the same row
     if (hxv == p.lo[0] - 1) hxv = p.hi[0] - 1;
@@ -123,6 +124,13 @@ __global__ void __launch_bounds__(256, MB)
   for (int j = 0; j < RY; ++j) {
     pc[j] = src + (long long)(z0 + 1) * S + yo(y + j) + xoff;
     ph[j] = src + (long long)z0 * S + yo(y + j) + (long long)hx * (long long)sizeof(T);
+    if (PUSH == 3) { // the x neighbour of the first / last compute cell may come from a dense received array [y][z]
+      const int side = (lane == 0 && x == p.lo[0]) ? 0 : ((lane == 31 && x + VX == p.hi[0]) ? 1 : -1);
+      if (side >= 0 && p.xghost_ptr[side]) {
+        ph[j] = p.xghost_ptr[side] + (long long)(y + j) * p.xghost_pitch[side] + (long long)z0 * (long long)sizeof(T);
+        phstep = (long long)sizeof(T);
+      }
+    }
     pw[j] = p.dst + (long long)z0 * S + (long long)(y + j) * P + (long long)x * (long long)sizeof(T);
   }
   int yu = y - 1, yd = y + RY;
@@ -168,6 +176,16 @@ __global__ void __launch_bounds__(256, MB)
         xpush = true;
       }
     }
+  }
+
+  // mode 3: the edge lane parks its face cell of every plane in shared memory; after the march its warp writes the
+  // row's whole chunk (<= 32 planes = 256 bytes) into the neighbour's dense array with one coalesced store
+  __shared__ T xstage[PUSH == 3 ? 2 : 1][PUSH == 3 ? 8 : 1][PUSH == 3 ? 32 : 1];
+  int xside = -1;
+  if (PUSH == 3 && row_ok[0]) {
+    if (lane == 0 && x == p.lo[0] && p.push_ptr[0] && p.xdense[0]) xside = 0;
+    if (lane == 31 && x + VX == p.hi[0] && p.push_ptr[1] && p.xdense[1]) xside = 1;
+    if (xside >= 0) xpush = true;
   }
 
   V A[RY], B[RY], C[RY];
@@ -243,6 +261,9 @@ __global__ void __launch_bounds__(256, MB)
             if (cell_ok & (1u << i)) reinterpret_cast<T *>(pw[j])[i] = out.v[i];
         }
       }
+      if (PUSH == 3) {
+        if (xpush) xstage[xside][warp][z - z0] = (xside == 0) ? out.v[0] : out.v[VX - 1];
+      }
       if (PUSH == 1) {
         if (xpush) { // two lanes per row
           T v = out.v[0];
@@ -253,7 +274,7 @@ __global__ void __launch_bounds__(256, MB)
         }
       }
       pc[j] += S;
-      ph[j] += S;
+      ph[j] += (PUSH == 3) ? phstep : S;
       pw[j] += S;
     }
     pu += S;
@@ -269,6 +290,18 @@ __global__ void __launch_bounds__(256, MB)
     step(C, A, B);
   }
 
+  if (PUSH == 3) {
+    // flush the staged x faces: warp-uniform (a warp belongs to one strip), one 8-byte element per lane and plane
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const int owner = side == 0 ? 0 : 31;
+      const bool mine = __shfl_sync(0xffffffffu, xside == side ? 1 : 0, owner) != 0;
+      if (!mine) continue;
+      __syncwarp();
+      if (lane < z1 - z0)
+        *reinterpret_cast<T *>(p.push_ptr[side] + (long long)y * p.push_pitch[side] + (long long)(z0 + lane) * (long long)sizeof(T)) = xstage[side][warp][lane];
+    }
+  }
   if (PUSH) {
     // y and z faces, after the loop: every lane re-reads the face cells IT stored in this chunk (its own writes: no
     // barrier, L2-resident) and stores them into the ghost row / plane of the neighbour.  Only the two edge rows of the
@@ -436,7 +469,9 @@ template <typename T, int VX, bool SHIFT> int launch_march_push(const JacobiPara
   const int tiles_z = (nz + p.zchunk - 1) / p.zchunk;
   const int tiles_y = (ny + 7) / 8;
   const long long blocks = (long long)tiles_x * tiles_y * tiles_z;
-  if (p.push_ptr[0] || p.push_ptr[1])
+  if (p.xdense[0] || p.xdense[1] || p.xghost_ptr[0] || p.xghost_ptr[1])
+    jacobi_march_kernel<T, VX, 1, 4, SHIFT, 3><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
+  else if (p.push_ptr[0] || p.push_ptr[1])
     jacobi_march_kernel<T, VX, 1, 4, SHIFT, 1><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
   else // no x face to push (periodic self-neighbour read in place, or nothing asked): the loop is the plain kernel's
     jacobi_march_kernel<T, VX, 1, 4, SHIFT, 2><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
@@ -596,6 +631,10 @@ int launch_jacobi_push(const JacobiParams &p_in, int dtype_size, cudaStream_t st
   // column is read by a vector load or a shuffle and the x faces are pushed into the ghost cells like any other face
   if (p.xwrap && !(!shift && p.x0a == p.lo[0] && (p.hi[0] - p.lo[0]) % (32 * vx) == 0)) p.xwrap = 0;
   if (p.xwrap) p.push_ptr[0] = p.push_ptr[1] = nullptr;
+  if (p.xdense[0] || p.xdense[1] || p.xghost_ptr[0] || p.xghost_ptr[1]) {
+    // dense x faces go through the edge lanes and a 32-plane shared-memory stage: same layout conditions as the wrap
+    if (shift || p.x0a != p.lo[0] || (p.hi[0] - p.lo[0]) % (32 * vx) != 0 || p.zchunk > 32) return -1;
+  }
   if (dtype_size == 8) {
     if (vx == 2) return shift ? launch_march_push<double, 2, true>(p, stream) : launch_march_push<double, 2, false>(p, stream);
     return launch_march_push<double, 1, false>(p, stream);

@@ -34,6 +34,14 @@ struct JacobiParams {
   // neighbour from the OPPOSITE face of src instead of from the ghost cells -- a pointer set up before the marching loop,
   // so that axis needs no exchange and no push at all
   int xwrap, ywrap;
+  // dense x faces between ranks (fused launch, mode 3): xdense[d] != 0 means push_ptr[d] is not a ghost column but a
+  // dense array [y][z] (z fastest, this subdomain's allocation coordinates; push_pitch[d] = bytes per row) in the
+  // NEIGHBOUR's memory: the column is staged in shared memory and written out as one 256-byte line per row and chunk
+  // instead of one 8-byte NVLink store per row and plane.  xghost_ptr[s]: the same kind of array received FROM the
+  // neighbour on side s, read by the edge lanes instead of the ghost column of src.
+  int xdense[2];
+  const char *xghost_ptr[2];
+  long long xghost_pitch[2];
 };
 
 // Up to 8 thin regions (the exterior slabs of one subdomain) updated by ONE launch.

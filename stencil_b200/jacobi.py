@@ -206,7 +206,7 @@ class Jacobi3D:
         output allocations (own memory, a peer GPU of this process, or another rank's IPC mapping)."""
         import os
 
-        from .domain import get_neighbor
+        from .domain import CopyPlan, box_copy, get_neighbor
 
         dd, h = self.dd, self.h
         r = dd.radius_
@@ -217,25 +217,95 @@ class Jacobi3D:
             raise RuntimeError("the fused jacobi schedule stores into peer memory: not available on the NCCL fallback")
         dirs = ((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1))
         # An x face is one 8-byte cell per row.  Pushed cell by cell into another GPU it costs 17 us per iteration through
-        # in-process peer access (fine) but 78 us through CUDA-IPC mappings; collecting the column in a dense array and
-        # shipping it between kernels, or leaving it to the copy engine between kernels, costs 30-70 us of serialised
-        # small launches (all measured on 2 x B200, profiles/README.md section 6).  So when an x face crosses RANKS the
-        # queued schedule (x faces staged by the copy engine, hidden behind the interior kernel) is the faster one, and
-        # this schedule is not used.  One decision for the whole job: every rank evaluates the same partition.
+        # in-process peer access (fine) but 78 us through CUDA-IPC mappings; shipping a dense copy between kernels, or
+        # leaving the x faces to the copy engine between kernels, costs 30-70 us of serialised small launches (all
+        # measured on 2 x B200, profiles/README.md section 6.1).  Across ranks the x column therefore travels as 256-byte
+        # lines written by the kernel itself (below); where that is not possible or not validated the queued schedule
+        # runs instead.  One decision for the whole job: every rank evaluates the same partition.
         part = dd.partition_
-        if any(dd._owner[tuple(i)][0] != dd._owner[tuple(get_neighbor(i, dv, part.dim))][0] for i in part.indices() for dv in dirs[:2]):
-            raise RuntimeError("x faces cross ranks: the queued schedule is faster than 8-byte stores through CUDA-IPC mappings")
-        self._fused_calls = []
+        x_crosses_ranks = any(dd._owner[tuple(i)][0] != dd._owner[tuple(get_neighbor(i, dv, part.dim))][0] for i in part.indices() for dv in dirs[:2])
+        # x faces between ranks as dense [y][z] arrays: the kernel stages its column in shared memory and writes one
+        # 256-byte line per row and chunk into the neighbour's receive array (double buffered by swap parity); the
+        # neighbour's edge lanes read their x ghosts from that array (kernel mode 3, sb_halo_push.x_dense / x_recv).
+        es = dd.domains()[0].elem_size(h.id)
+        strip = 32 * (16 // es)
+        # SB_FUSED_IPC: "1" always (layout permitting), "0" never, unset = where it was validated AND measured faster on
+        # B200 this round: partitions whose z axis stays inside a rank (N = 2: 0.398 vs 0.431 ms queued; N = 4: 0.431 vs
+        # 0.434).  N = 8 splits z across ranks as well; that combination has not been run yet, so it keeps the queued schedule.
+        mode = os.environ.get("SB_FUSED_IPC", "")
+        z_in_rank = all(dd._owner[tuple(i)][0] == dd._owner[tuple(get_neighbor(i, dv, part.dim))][0] for i in part.indices() for dv in dirs[4:])
+        want = mode == "1" or (mode == "" and z_in_rank)
+        dense = x_crosses_ranks and want and all(
+            part.subdomain_size(i)[0] % strip == 0 and ((part.subdomain_size(i)[0] + r.x(-1) + r.x(1)) * es) % 16 == 0 for i in part.indices()
+        ) and all((d.pitched(h.id, w).ptr + r.x(-1) * es) % 16 == 0 for d in dd.domains() for w in ("curr", "next"))
+        if dd._remote is not None:
+            from . import dist as _dist
+
+            dense = all(_dist.all_gather_object(bool(dense)))
+        if x_crosses_ranks and not dense:
+            raise RuntimeError("x faces cross ranks and the dense x path does not apply: the queued schedule is the faster one")
+        self._xbuf, self._xopened = [], []
+        recv, remote_recv = {}, {}
+        L = lib()
+        if dense:
+            from . import dist as _dist
+
+            for di, d in enumerate(dd.domains()):
+                idx = tuple(dd.domain_idx_[di])
+                raw = d.raw_size()
+                for side, dv in enumerate(dirs[:2]):
+                    nidx = tuple(get_neighbor(idx, dv, part.dim))
+                    if dd._owner[nidx][0] == dd._world.rank:
+                        continue
+                    bufs = []
+                    for _ in range(2):  # one receive array per swap parity
+                        pbuf = C.c_void_p()
+                        check(L.sb_malloc(C.byref(pbuf), raw[1] * raw[2] * es, d.gpu()))
+                        check(L.sb_memset(pbuf, 0, raw[1] * raw[2] * es, d.gpu(), None))
+                        bufs.append(int(pbuf.value))
+                        self._xbuf.append((int(pbuf.value), d.gpu()))
+                    recv[(di, side)] = bufs
+            mine = {}
+            for (di, side), ptrs in recv.items():
+                handles = []
+                for ptr in ptrs:
+                    hb = (C.c_char * 64)()
+                    check(L.sb_ipc_export(C.c_void_p(ptr), hb))
+                    handles.append(bytes(hb))
+                mine[(tuple(dd.domain_idx_[di]), side)] = handles
+            wanted = set()  # the receive arrays my subdomains write into: side 1 - s of my neighbour on side s
+            for di in range(len(dd.domains())):
+                idx = tuple(dd.domain_idx_[di])
+                for s_, dv in enumerate(dirs[:2]):
+                    nidx = tuple(get_neighbor(idx, dv, part.dim))
+                    if dd._owner[nidx][0] != dd._world.rank:
+                        wanted.add((nidx, 1 - s_))
+            for rank, table in enumerate(_dist.all_gather_object(mine)):
+                if rank == dd._world.rank:
+                    continue
+                for key, handles in table.items():
+                    key = (tuple(key[0]), key[1])
+                    if key not in wanted:
+                        continue
+                    ptrs = []
+                    for hnd in handles:
+                        out = C.c_void_p()
+                        check(L.sb_ipc_import(hnd, dd.domains()[0].gpu(), C.byref(out)))
+                        self._xopened.append(int(out.value))
+                        ptrs.append(int(out.value))
+                    remote_recv[key] = ptrs
+        self._fused_calls, self._init_plans = [], []
         self._fused_nbr_slots = []  # in-process neighbours of each local subdomain (stream dependencies)
         for rel in (0, 1):
             absolute = (self._parity0 + rel) & 1
-            per_dom = []
+            per_dom, inits = [], []
             for di, d in enumerate(dd.domains()):
                 idx = tuple(dd.domain_idx_[di])
                 src = d.pitched(h.id, "curr" if rel == 0 else "next")
                 dst = d.pitched(h.id, "next" if rel == 0 else "curr")
                 push = HaloPush()
                 slots = set()
+                init_copies = []
                 for k, dv in enumerate(dirs):
                     nidx = get_neighbor(idx, dv, dd.partition_.dim)
                     # the neighbour's NEXT buffer at this parity is its curr buffer of the other parity
@@ -248,15 +318,32 @@ class Jacobi3D:
                         raw = dd._remote.raw_of(nidx)
                     push.nbr[k] = Pitched(pn.ptr, pn.pitch, pn.ysize)
                     push.nbr_zsize[k] = raw[2]
+                    if k < 2 and dense and rank != dd._world.rank:
+                        myraw = d.raw_size()
+                        target = remote_recv[(tuple(nidx), 1 - k)]
+                        # iteration `rel` writes what the neighbour reads in the next one (parity rel ^ 1)
+                        push.nbr[k] = Pitched(target[rel ^ 1], es, myraw[1])
+                        push.nbr_zsize[k] = myraw[2]
+                        push.x_dense[k] = 1
+                        push.x_recv[k] = recv[(di, k)][rel]
+                        # before the first fused iteration at this parity: the neighbour needs my column of curr itself
+                        lo3 = (r.x(-1), r.y(-1), r.z(-1))
+                        sz3 = d.size()
+                        xcol = lo3[0] if k == 0 else lo3[0] + sz3[0] - 1
+                        for zz in range(lo3[2], lo3[2] + sz3[2]):
+                            col = Pitched(target[rel] + zz * es, myraw[2] * es, myraw[1])  # element (0, y, 0) -> [y][zz]
+                            init_copies.append(box_copy(col, (0, lo3[1], 0), src, (xcol, lo3[1], zz), (1, sz3[1], 1), es))
                     if os.environ.get("SB_DEBUG_NOPUSH"):  # timing diagnostics only: results are wrong
                         push.nbr[k] = Pitched(None, 0, 0)
                 creg = d.get_compute_region()
                 clo, chi = i3(self.creg[0]), i3(self.creg[1])
                 pack = (dst, src, d.elem_size(h.id), i3(d.accessor_origin()), i3(creg[0]), i3(creg[1]), clo, chi, push, stream_ptr(self.streams[di]))
                 per_dom.append(pack)
+                inits.append(CopyPlan(d.gpu(), init_copies) if init_copies else None)
                 if rel == 0:
                     self._fused_nbr_slots.append(sorted(slots))
             self._fused_calls.append(per_dom)
+            self._init_plans.append(inits)
         self._fn_fused = lib().sb_jacobi3d_fused
         self._fused_epoch = 0
         self._ev_fused = None
@@ -288,6 +375,11 @@ class Jacobi3D:
         if not self._ghosts_current:
             self.synchronize()
             dd.exchange()  # ghost cells of curr, once; afterwards every iteration leaves them filled for the next
+            rel0 = (dd._parity - self._parity0) & 1
+            for di, plan in enumerate(self._init_plans[rel0]):  # dense x columns for neighbour ranks (SB_FUSED_IPC=1)
+                if plan is not None:
+                    plan.launch(self.streams[di])
+            self.synchronize()
             if dd._remote is not None:
                 import torch.distributed as td
 
@@ -327,8 +419,24 @@ class Jacobi3D:
         dd.swap()
 
     def close(self) -> None:
-        """Drain the queued work (everything else is owned by DistributedDomain.close())."""
+        """Drain the queued work; release the dense x receive arrays of the SB_FUSED_IPC experiment."""
         self.synchronize()
+        if not getattr(self, "_xbuf", None) and not getattr(self, "_xopened", None):
+            return
+        import torch.distributed as td
+
+        for plans in getattr(self, "_init_plans", []):
+            for p in plans:
+                if p is not None:
+                    p.destroy()
+        self._init_plans = []
+        td.barrier()  # nobody unmaps or frees while a neighbour could still write
+        for ptr in self._xopened:
+            lib().sb_ipc_close(C.c_void_p(ptr), self.dd.domains()[0].gpu())
+        td.barrier()
+        for ptr, dev in self._xbuf:
+            lib().sb_free(C.c_void_p(ptr), dev)
+        self._xbuf, self._xopened = [], []
 
     def synchronize(self) -> None:
         """Wait for the compute streams (bin/jacobi3d.cu:363-365)."""
