@@ -37,6 +37,34 @@ def scaled_size(x: int, y: int, z: int, num_subdoms: int) -> Tuple[int, int, int
     return x, y, z
 
 
+FACE_DIRS = ((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1))
+
+
+def fused_x_mode(part, owner, elem_size: int, radius: Radius, mode: str = "") -> str:
+    """How the fused schedule moves x faces for a given partition / ownership (pure: every rank computes the same).
+
+    "direct": no x face crosses ranks -- the kernel stores boundary cells into the neighbour's ghost cells (own memory or
+              a peer GPU of this process) or reads a periodic self-neighbour in place;
+    "dense":  x faces cross ranks and travel as 256-byte lines into dense receive arrays (kernel mode 3): needs whole warp
+              strips along x and rows of one 16-byte phase; chosen by default only where it was validated and measured
+              faster this round (z faces inside a rank: 2 and 4 ranks), always with mode "1", never with mode "0";
+    "queued": fall back to the queued schedule (Jacobi3D.step_async)."""
+    from .domain import get_neighbor
+
+    def crosses(dirs):
+        return any(owner[tuple(i)][0] != owner[tuple(get_neighbor(i, dv, part.dim))][0] for i in part.indices() for dv in dirs)
+
+    if not crosses(FACE_DIRS[:2]):
+        return "direct"
+    strip = 32 * (16 // elem_size)
+    layout = all(
+        part.subdomain_size(i)[0] % strip == 0 and ((part.subdomain_size(i)[0] + radius.x(-1) + radius.x(1)) * elem_size) % 16 == 0
+        for i in part.indices()
+    )
+    want = mode == "1" or (mode == "" and not crosses(FACE_DIRS[4:]))
+    return "dense" if (want and layout and mode != "0") else "queued"
+
+
 class Jacobi3D:
     def __init__(self, dd: DistributedDomain, h: DataHandle, overlap: bool = True):
         import torch
@@ -223,21 +251,13 @@ class Jacobi3D:
         # lines written by the kernel itself (below); where that is not possible or not validated the queued schedule
         # runs instead.  One decision for the whole job: every rank evaluates the same partition.
         part = dd.partition_
-        x_crosses_ranks = any(dd._owner[tuple(i)][0] != dd._owner[tuple(get_neighbor(i, dv, part.dim))][0] for i in part.indices() for dv in dirs[:2])
+        es = dd.domains()[0].elem_size(h.id)
+        xmode = fused_x_mode(part, dd._owner, es, r, os.environ.get("SB_FUSED_IPC", ""))
+        x_crosses_ranks = xmode != "direct"
         # x faces between ranks as dense [y][z] arrays: the kernel stages its column in shared memory and writes one
         # 256-byte line per row and chunk into the neighbour's receive array (double buffered by swap parity); the
         # neighbour's edge lanes read their x ghosts from that array (kernel mode 3, sb_halo_push.x_dense / x_recv).
-        es = dd.domains()[0].elem_size(h.id)
-        strip = 32 * (16 // es)
-        # SB_FUSED_IPC: "1" always (layout permitting), "0" never, unset = where it was validated AND measured faster on
-        # B200 this round: partitions whose z axis stays inside a rank (N = 2: 0.398 vs 0.431 ms queued; N = 4: 0.431 vs
-        # 0.434).  N = 8 splits z across ranks as well; that combination has not been run yet, so it keeps the queued schedule.
-        mode = os.environ.get("SB_FUSED_IPC", "")
-        z_in_rank = all(dd._owner[tuple(i)][0] == dd._owner[tuple(get_neighbor(i, dv, part.dim))][0] for i in part.indices() for dv in dirs[4:])
-        want = mode == "1" or (mode == "" and z_in_rank)
-        dense = x_crosses_ranks and want and all(
-            part.subdomain_size(i)[0] % strip == 0 and ((part.subdomain_size(i)[0] + r.x(-1) + r.x(1)) * es) % 16 == 0 for i in part.indices()
-        ) and all((d.pitched(h.id, w).ptr + r.x(-1) * es) % 16 == 0 for d in dd.domains() for w in ("curr", "next"))
+        dense = xmode == "dense" and all((d.pitched(h.id, w).ptr + r.x(-1) * es) % 16 == 0 for d in dd.domains() for w in ("curr", "next"))
         if dd._remote is not None:
             from . import dist as _dist
 

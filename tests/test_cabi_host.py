@@ -120,3 +120,35 @@ def test_interior_exterior_vs_oracle():
 def test_neighbor_wrap_vs_reference():
     for p, lim, w in GOLD["wrap"]:
         assert list(sb.get_neighbor(tuple(p), (0, 0, 0), tuple(lim))) == w
+
+
+def test_fused_schedule_choice_per_partition():
+    """Jacobi3D picks how x faces travel in the fused schedule from the partition and the ownership table alone (every
+    rank evaluates the same function): direct pushes while x stays inside a rank, dense 256-byte lines across ranks where
+    the layout allows it and the combination was validated (z inside a rank), else the queued schedule."""
+    from stencil_b200.domain import Partition, Radius
+    from stencil_b200.jacobi import fused_x_mode
+
+    r = Radius.face_edge_corner(1, 0, 0)
+
+    def owners(part, per_rank):
+        return {tuple(idx): (k // per_rank, k % per_rank) for k, idx in enumerate(part.indices())}
+
+    one = Partition((512, 512, 512), r, 1, 1)
+    assert fused_x_mode(one, owners(one, 1), 8, r) == "direct"
+    two = Partition((1024, 512, 512), r, 1, 2)
+    assert tuple(two.dim) == (2, 1, 1)
+    assert fused_x_mode(two, owners(two, 2), 8, r) == "direct"  # one process x 2 GPUs: peer access
+    assert fused_x_mode(two, owners(two, 1), 8, r) == "dense"  # torchrun, 2 ranks
+    assert fused_x_mode(two, owners(two, 1), 8, r, "0") == "queued"
+    four = Partition((1024, 1024, 512), r, 1, 4)
+    assert tuple(four.dim) == (2, 2, 1) and fused_x_mode(four, owners(four, 1), 8, r) == "dense"
+    eight = Partition((1024, 1024, 1024), r, 1, 8)
+    assert tuple(eight.dim) == (2, 2, 2)
+    assert fused_x_mode(eight, owners(eight, 1), 8, r) == "queued"  # z crosses ranks: not validated this round
+    assert fused_x_mode(eight, owners(eight, 1), 8, r, "1") == "dense"
+    # 48 cells along x per rank are not whole warp strips (64 FP64 cells): never dense
+    small = Partition((96, 48, 48), r, 1, 2)
+    assert fused_x_mode(small, owners(small, 1), 8, r, "1") == "queued"
+    # FP32: strips of 128 cells, and 514-float rows alternate between two 16-byte phases
+    assert fused_x_mode(two, owners(two, 1), 4, r, "1") == "queued"
