@@ -152,3 +152,24 @@ def test_fused_schedule_choice_per_partition():
     assert fused_x_mode(small, owners(small, 1), 8, r, "1") == "queued"
     # FP32: strips of 128 cells, and 514-float rows alternate between two 16-byte phases
     assert fused_x_mode(two, owners(two, 1), 4, r, "1") == "queued"
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The Python mirrors of the C ABI structs have the size the header gives them (gcc compiles a probe against
+    include/stencil_b200.h): a field added on one side only would shift every later argument silently."""
+    import ctypes as C
+    import os
+    import subprocess
+
+    from stencil_b200._lib import AstarothParams, BoxCopy, HaloPush, Pitched
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "probe.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "stencil_b200.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu\\n", sizeof(sb_pitched), sizeof(sb_box_copy), sizeof(sb_halo_push), sizeof(sb_astaroth_params)); return 0; }\n'
+    )
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [C.sizeof(Pitched), C.sizeof(BoxCopy), C.sizeof(HaloPush), C.sizeof(AstarothParams)]
