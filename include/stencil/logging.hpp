@@ -1,9 +1,12 @@
 #pragma once
-// LOG_SPEW / DEBUG / INFO / WARN / ERROR / FATAL to stderr, filtered at compile time by
-// STENCIL_OUTPUT_LEVEL (5 = everything ... 0 = fatal only).  LOG_FATAL exits with status 1.
+// LOG_SPEW / LOG_DEBUG / LOG_INFO / LOG_WARN / LOG_ERROR / LOG_FATAL(stream expression)
+// One line per message on stderr: TAG[file:line]{rank} text.  STENCIL_OUTPUT_LEVEL selects at compile time how chatty
+// the build is (5: everything ... 0: fatal only; default 3).  A message is composed in a local buffer and written with
+// a single insertion so lines of different ranks do not interleave mid-line.  LOG_FATAL terminates with status 1.
 
 #include <cstdlib>
 #include <iostream>
+#include <sstream>
 
 #include "stencil/mpi.hpp"
 
@@ -11,43 +14,33 @@
 #define STENCIL_OUTPUT_LEVEL 3
 #endif
 
-#define STENCIL_LOG_LINE(tag, x)                                                                                       \
-  std::cerr << tag "[" << __FILE__ << ":" << __LINE__ << "]{" << mpi::world_rank() << "} " << x << "\n";
+namespace stencil {
+namespace detail {
+inline void emit_log(const char *tag, const char *file, int line, const std::string &text) {
+  std::ostringstream msg;
+  msg << tag << '[' << file << ':' << line << "]{" << mpi::world_rank() << "} " << text << '\n';
+  std::cerr << msg.str();
+}
+} // namespace detail
+} // namespace stencil
 
-#if STENCIL_OUTPUT_LEVEL >= 5
-#define LOG_SPEW(x) STENCIL_LOG_LINE("SPEW", x)
-#else
-#define LOG_SPEW(x)
-#endif
+// `expr` is a chain of << operands, e.g. LOG_INFO("n=" << n)
+#define STENCIL_LOG_AT(level, tag, expr)                                                                               \
+  do {                                                                                                                 \
+    if ((level) <= STENCIL_OUTPUT_LEVEL) {                                                                             \
+      std::ostringstream stencil_log_buf_;                                                                             \
+      stencil_log_buf_ << expr;                                                                                        \
+      stencil::detail::emit_log(tag, __FILE__, __LINE__, stencil_log_buf_.str());                                      \
+    }                                                                                                                  \
+  } while (0)
 
-#if STENCIL_OUTPUT_LEVEL >= 4
-#define LOG_DEBUG(x) STENCIL_LOG_LINE("DEBUG", x)
-#else
-#define LOG_DEBUG(x)
-#endif
-
-#if STENCIL_OUTPUT_LEVEL >= 3
-#define LOG_INFO(x) STENCIL_LOG_LINE("INFO", x)
-#else
-#define LOG_INFO(x)
-#endif
-
-#if STENCIL_OUTPUT_LEVEL >= 2
-#define LOG_WARN(x) STENCIL_LOG_LINE("WARN", x)
-#else
-#define LOG_WARN(x)
-#endif
-
-#if STENCIL_OUTPUT_LEVEL >= 1
-#define LOG_ERROR(x) STENCIL_LOG_LINE("ERROR", x)
-#else
-#define LOG_ERROR(x)
-#endif
-
-#if STENCIL_OUTPUT_LEVEL >= 0
-#define LOG_FATAL(x)                                                                                                   \
-  STENCIL_LOG_LINE("FATAL", x)                                                                                         \
-  exit(1);
-#else
-#define LOG_FATAL(x) exit(1);
-#endif
+#define LOG_SPEW(expr) STENCIL_LOG_AT(5, "SPEW", expr)
+#define LOG_DEBUG(expr) STENCIL_LOG_AT(4, "DEBUG", expr)
+#define LOG_INFO(expr) STENCIL_LOG_AT(3, "INFO", expr)
+#define LOG_WARN(expr) STENCIL_LOG_AT(2, "WARN", expr)
+#define LOG_ERROR(expr) STENCIL_LOG_AT(1, "ERROR", expr)
+#define LOG_FATAL(expr)                                                                                                \
+  do {                                                                                                                 \
+    STENCIL_LOG_AT(0, "FATAL", expr);                                                                                  \
+    std::exit(1);                                                                                                      \
+  } while (0)

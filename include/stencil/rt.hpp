@@ -1,25 +1,49 @@
 #pragma once
-// rt::time / rt::launch / mpirt::time: call-through wrappers with (optional) API timing hooks.
+// Call-through helpers the reference API exposes for "timed" CUDA / MPI calls:
+//   rt::time(fn, args...)                      -> cudaError_t
+//   rt::launch(kernel, grid, block, shmem, stream, args...)
+//   mpirt::time(fn, args...)                   -> int
+// Here the accounting is a scope guard around the call (stencil::detail::ApiScope); with per-call accounting
+// disabled (the default, like the reference's Release build) the guard is empty and the helpers cost nothing.
 
 #include <cuda_runtime.h>
 
+#include <utility>
+
 #include "stencil/timer.hpp"
+
+namespace stencil {
+namespace detail {
+
+#ifdef STENCIL_TIME_API_CALLS
+struct ApiScope {
+  Timer &t_;
+  explicit ApiScope(Timer &t) : t_(t) { t_.resume(); }
+  ~ApiScope() { t_.pause(); }
+};
+#else
+struct ApiScope {
+  explicit ApiScope(Timer &) {}
+};
+#endif
+
+} // namespace detail
+} // namespace stencil
 
 namespace rt {
 
-template <typename Fn, typename... Args> cudaError_t time(Fn fn, Args... args) {
-  CR_TIC();
-  const cudaError_t err = fn(args...);
-  CR_TOC();
-  return err;
+template <typename Call, typename... Ts> inline cudaError_t time(Call call, Ts... ts) {
+  stencil::detail::ApiScope scope(timers::cudaRuntime);
+  (void)scope;
+  return call(ts...);
 }
 
-#if __CUDACC__
-template <typename Fn, typename... Args>
-void launch(Fn fn, const dim3 &grid, const dim3 &block, const int shmem, cudaStream_t stream, Args... args) {
-  CR_TIC();
-  fn<<<grid, block, shmem, stream>>>(args...);
-  CR_TOC();
+#if defined(__CUDACC__)
+template <typename Kernel, typename... Ts>
+inline void launch(Kernel kernel, const dim3 &grid, const dim3 &block, const int shmem, cudaStream_t stream, Ts... ts) {
+  stencil::detail::ApiScope scope(timers::cudaRuntime);
+  (void)scope;
+  kernel<<<grid, block, shmem, stream>>>(ts...);
 }
 #endif
 
@@ -27,11 +51,10 @@ void launch(Fn fn, const dim3 &grid, const dim3 &block, const int shmem, cudaStr
 
 namespace mpirt {
 
-template <typename Fn, typename... Args> int time(Fn fn, Args... args) {
-  MPI_TIC();
-  const int err = fn(args...);
-  MPI_TOC();
-  return err;
+template <typename Call, typename... Ts> inline int time(Call call, Ts... ts) {
+  stencil::detail::ApiScope scope(timers::mpi);
+  (void)scope;
+  return call(ts...);
 }
 
 } // namespace mpirt

@@ -1,16 +1,16 @@
 #include "stencil/timer.hpp"
 
-double Timer::get_elapsed() {
-  pause();
-  return total_.count();
-}
+namespace timers {
+Timer cudaRuntime; // time inside CUDA runtime calls (when STENCIL_TIME_API_CALLS is defined)
+Timer mpi;         // time inside MPI calls
+} // namespace timers
 
 void Timer::clear() {
-  pause();
-  total_ = std::chrono::duration<double>(0);
+  running_ = false;
+  accumulated_ = std::chrono::duration<double>(0.0);
 }
 
-namespace timers {
-Timer cudaRuntime;
-Timer mpi;
-} // namespace timers
+double Timer::get_elapsed() {
+  pause();
+  return accumulated_.count();
+}

@@ -1,15 +1,17 @@
 #include "stencil/topology.hpp"
 
-Topology::Topology() : Topology(Dim3(0, 0, 0), Boundary::NONE) {}
-
 Topology::OptionalNeighbor Topology::get_neighbor(const Dim3 &index, const Dim3 &dir) const noexcept {
-  assert(dir.all_gt(-2) && dir.all_lt(2));
-  assert(index.all_ge(0));
-  if (Boundary::PERIODIC != boundary_) {
-    LOG_FATAL("unexpected Boundary type");
+  assert(index.all_ge(0) && "subdomain indices are non-negative");
+  assert(dir.all_gt(-2) && dir.all_lt(2) && "a direction has components in {-1, 0, +1}");
+  OptionalNeighbor answer;
+  switch (kind_) {
+  case Boundary::PERIODIC:
+    // a periodic grid wraps: stepping off one face re-enters through the opposite one
+    answer.index = (index + dir).wrap(grid_);
+    answer.exists = true;
+    break;
+  default:
+    LOG_FATAL("Topology::get_neighbor: only periodic grids are supported");
   }
-  OptionalNeighbor nbr;
-  nbr.exists = true; // periodic: everybody has a neighbour everywhere
-  nbr.index = (index + dir).wrap(extent_);
-  return nbr;
+  return answer;
 }
