@@ -9,12 +9,12 @@ reference (AcReal = double) and FP32 as well here.  The kernel is `sb_astaroth_s
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence
 
 import numpy as np
 
 from ._lib import AstarothParams, check, i3, lib, stream_ptr
-from .domain import DataHandle, DistributedDomain, LocalDomain
+from .domain import DataHandle, DistributedDomain
 
 FIELDS = ("lnrho", "uux", "uuy", "uuz", "ax", "ay", "az", "entropy")
 NGHOST = 3  # STENCIL_ORDER / 2, astaroth/astaroth.h:8-9

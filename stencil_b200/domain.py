@@ -25,14 +25,13 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
-import itertools
 import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import _lib
-from ._lib import BoxCopy, I3, I27, Pitched, check, i3, lib, o3, stream_ptr, t3
+from ._lib import BoxCopy, I27, Pitched, check, i3, lib, o3, stream_ptr, t3
 
 Vec = Tuple[int, int, int]
 

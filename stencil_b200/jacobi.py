@@ -9,7 +9,7 @@ handful of foreign calls.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Tuple
+from typing import Tuple
 
 import numpy as np
 

@@ -6,7 +6,6 @@ import json
 import os
 import re
 
-import numpy as np
 import pytest
 
 import stencil_b200 as sb

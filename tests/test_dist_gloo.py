@@ -28,7 +28,6 @@ def _worker(rank, world, port, size, rname, dtypes, out_q):
         td.init_process_group("gloo", rank=rank, world_size=world)
         import stencil_b200 as sb
         from gpu_util import oracle_radius
-        from oracle import geometry as g
         from oracle import np_oracle as no
         from stencil_b200 import dist
 

@@ -8,7 +8,7 @@ import pytest
 import stencil_b200 as sb
 from oracle import geometry as g
 from oracle import np_oracle as no
-from stencil_b200._lib import BoxCopy, Pitched, check, i3, lib
+from stencil_b200._lib import Pitched, check, i3, lib
 from gpu_util import DevArray
 
 pytestmark = pytest.mark.gpu
