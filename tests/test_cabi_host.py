@@ -172,3 +172,25 @@ def test_ctypes_structs_match_the_header(tmp_path):
     subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert sizes == [C.sizeof(Pitched), C.sizeof(BoxCopy), C.sizeof(HaloPush), C.sizeof(AstarothParams)]
+
+
+def test_allocation_lead_rule(monkeypatch):
+    """LocalDomain.lead_bytes: when all rows share one 16-byte phase the allocation starts so that
+    the first COMPUTE cell is 16-byte aligned; rows with alternating phase (FP32, 514 cells) keep the reference placement."""
+    import numpy as np
+
+    from stencil_b200.domain import LocalDomain, Radius
+
+    def lead(n, r, dtype):
+        d = LocalDomain((n, n, n), (0, 0, 0), 0)
+        d.set_radius(Radius.constant(r))
+        d.add_data(dtype)
+        return d.lead_bytes(np.dtype(dtype).itemsize)
+
+    assert lead(512, 1, np.float64) == 8  # row = 514 * 8 = 4112 B = 16 * 257; first compute cell 8 B in
+    assert lead(512, 2, np.float64) == 0  # already aligned
+    assert lead(512, 3, np.float64) == 8
+    assert lead(512, 1, np.float32) == 0  # 2056 B rows alternate between two phases: no single lead helps
+    assert lead(510, 1, np.float32) == 12  # 512 floats per row: one phase, first compute cell 4 B in
+    monkeypatch.setenv("SB_ALLOC_ALIGN", "0")
+    assert lead(512, 1, np.float64) == 0
