@@ -20,7 +20,7 @@ APIDEFS   := -DSTENCIL_USE_MPI=1 -DSTENCIL_USE_CUDA=1 -DSTENCIL_USE_CUDA_AWARE_M
 APIINC    := -Iinclude -Iinclude/mpi_shim -I/usr/local/cuda/include/nvtx3
 APIFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -rdc=true --expt-extended-lambda -Xcompiler -fPIC -Xcompiler -Wall \
              -Xcompiler -Wno-comment -x cu $(APIDEFS) $(APIINC)
-APISRC    := src/compat_kernels.cu src/local_domain.cu src/packer.cu src/translator.cu src/stencil.cu \
+APISRC    := src/compat_kernels.cu src/local_domain.cu src/packer.cu src/translator.cu src/stencil.cu src/jacobi3d.cu \
              src/numeric.cpp src/timer.cpp src/rcstream.cpp src/topology.cpp src/gpu_topology.cpp \
              src/placement_intranoderandom.cpp src/mpi_shim.cpp
 APIOBJ    := $(patsubst src/%,build/api/%.o,$(APISRC))
@@ -86,6 +86,14 @@ bin/test_cpu: $(patsubst %,build/drv/t_%.o,$(TESTCPU)) $(LIBA)
 	@mkdir -p bin
 	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/t_%.o,$(TESTCPU)) $(LIBA)
 
+# our own driver: the reference's jacobi3d loop over stencil::FusedJacobi3d (no reference sources involved)
+build/drv/jacobi3d_b200.o: drivers/jacobi3d_b200.cu $(wildcard include/stencil/*)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(filter-out -I$(REF)/thirdparty -I$(REF)/bin,$(DRVFLAGS)) -c $< -o $@
+bin/jacobi3d_b200: build/drv/jacobi3d_b200.o $(LIBA)
+	@mkdir -p bin
+	$(NVCC) $(DRVLINK) -o $@ $< $(LIBA)
+
 # the baseline exchange driver (oracle/ref/ref_exchange_uniform.cu) against OUR library
 build/drv/exchange_uniform.o: oracle/ref/ref_exchange_uniform.cu $(wildcard include/stencil/*)
 	@mkdir -p $(dir $@)
@@ -117,7 +125,7 @@ bin/astaroth_b200: build/drv/astro_astaroth.o build/drv/astro_astaroth_utils.o b
 	@mkdir -p bin
 	$(NVCC) $(DRVLINK) -o $@ build/drv/astro_astaroth.o build/drv/astro_astaroth_utils.o build/drv/astro_b200_kernels.o build/drv/astro_statistics.o $(LIBA)
 
-drivers: $(patsubst %,bin/%,$(DRIVERS)) bin/test_cuda bin/test_cpu bin/exchange_uniform bin/astaroth bin/astaroth_b200 bin/test_exchange_multigpu
+drivers: bin/jacobi3d_b200 $(patsubst %,bin/%,$(DRIVERS)) bin/test_cuda bin/test_cpu bin/exchange_uniform bin/astaroth bin/astaroth_b200 bin/test_exchange_multigpu
 
 oracle:
 	$(MAKE) -C oracle

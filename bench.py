@@ -39,6 +39,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-overlap", action="store_true")
+    p.add_argument("--no-exchange-bench", action="store_true", help="skip the halo-exchange latency leg (BASELINE metric part 2, configs[2])")
+    p.add_argument("--no-parity", action="store_true", help="skip the bit-exact check against the oracle that follows the timed region")
     p.add_argument("--schedule", default="fused", choices=["fused", "queued", "host-sync"],
                    help="fused: one kernel per iteration = jacobi update + halo push into the neighbours' ghost cells (Jacobi3D.step_fused); "
                    "queued: interior || exchange -> exterior with CUDA-event dependencies (step_async); host-sync: the reference's loop (step)")
@@ -112,77 +114,15 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-class CpuJacobi:
-    """The oracle port of the same loop on one periodic 512^3 subdomain (C + OpenMP, oracle/stencil_oracle.c).
-    Used for `cpu_baseline` and for `--impl reference` (the reference has no runnable
-    CPU path; BASELINE.md 2a: the CPU baseline is this restatement)."""
+def time_cpu(n, dtype_name, steps, warmup, budget_s=0.0):
+    """The oracle port of the same loop on one periodic n^3 subdomain (C + OpenMP, oracle/stencil_oracle.c), timed in its
+    own process with a pinned OpenMP environment (oracle/cpu_bench.py: one thread per physical core of the affinity mask,
+    capped by the cgroup quota; OMP_PROC_BIND=close, OMP_PLACES=cores; first touch with the compute loops' schedule).
+    Used for `cpu_baseline` and for `--impl reference` (SURVEY.md fact 1: the reference has no runnable CPU path;
+    BASELINE.md 2a: the CPU baseline is this restatement)."""
+    from oracle import cpu_bench
 
-    def __init__(self, n: int, dtype):
-        from oracle import c_oracle as co
-        from oracle import geometry as g
-
-        self.co, self.g, self.n = co, g, n
-        self.r = g.Radius.face_edge_corner(1, 0, 0)
-        raw = g.raw_size((n, n, n), self.r)
-        self.cur = np.zeros(raw[::-1], dtype=dtype)
-        self.nxt = np.zeros(raw[::-1], dtype=dtype)
-        co.fill(self.cur, (1, 1, 1), (n, n, n), 0.5)
-        self.interior = g.get_interior((0, 0, 0), (n, n, n), self.r)
-        self.exterior = g.get_exterior((0, 0, 0), (n, n, n), self.r)
-        self.plan = g.plan_sends((1, 1, 1), {(0, 0, 0): (n, n, n)}, self.r)
-        self._mk()
-
-    def _mk(self):
-        self.copies = [
-            self.co.make_copies([(a, m["dst_pos"], a, m["src_pos"], m["ext"]) for m in self.plan]) for a in (self.cur, self.nxt)
-        ]
-        self.par = 0
-
-    def step(self):
-        co, n = self.co, self.n
-        cur, nxt = (self.cur, self.nxt) if self.par == 0 else (self.nxt, self.cur)
-        creg = ((0, 0, 0), (n, n, n))
-        co.jacobi_region(nxt, cur, (-1, -1, -1), *self.interior, *creg)
-        co.translate_many(*self.copies[self.par])
-        for lo, hi in self.exterior:
-            co.jacobi_region(nxt, cur, (-1, -1, -1), lo, hi, *creg)
-        self.par ^= 1
-
-    def current(self):
-        return self.cur if self.par == 0 else self.nxt
-
-
-def physical_cores() -> int:
-    try:
-        import psutil
-
-        n = psutil.cpu_count(logical=False)
-        if n:
-            return int(n)
-    except Exception:
-        pass
-    return max(1, (os.cpu_count() or 2) // 2)
-
-
-def time_cpu(n, dtype, steps, warmup, budget_s=None):
-    from oracle import c_oracle as co
-
-    # all physical cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank; with one thread
-    # per hyperthread the OpenMP port measured 14x slower on the 64-core / 128-thread GPU boxes)
-    co.set_num_threads(physical_cores())
-    cj = CpuJacobi(n, dtype)
-    for _ in range(warmup):
-        cj.step()
-    times = []
-    t_begin = time.perf_counter()
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        cj.step()
-        times.append(time.perf_counter() - t0)
-        if budget_s is not None and time.perf_counter() - t_begin > budget_s:
-            break
-    mean = float(np.mean(times))
-    return {"value": n**3 / mean, "ms_per_step": mean * 1e3, "steps": len(times), "cores": co.num_threads()}
+    return cpu_bench.run_in_subprocess(n, dtype_name, steps, warmup, budget_s)
 
 
 def cpu_model():
@@ -199,9 +139,8 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path = the oracle port (see CpuJacobi)."""
     if rank != 0:
         return
-    dtype = np.float64 if args.dtype == "f64" else np.float32
     n = args.size
-    res = time_cpu(n, dtype, args.steps, max(args.warmup, 1))
+    res = time_cpu(n, args.dtype, args.steps, max(args.warmup, 1))
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -227,11 +166,102 @@ def run_reference(args, rank, world):
             "cores": res["cores"],
             "kind": "port",
             "sample": f"{res['steps']} full iterations of {n}^3 (interior + 6-face periodic exchange + exterior)",
+            "host": res["host"],
+            "omp": res["omp"],
         },
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- halo exchange leg
+def trimean(v):
+    q1, q2, q3 = np.percentile(np.asarray(v, dtype=np.float64), [25, 50, 75])
+    return float((q1 + 2 * q2 + q3) / 4)
+
+
+def halo_exchange_metric(rank, world, gpus, ngpu, iters=30):
+    """BASELINE metric part 2 / configs[2]: `dd.exchange(); dd.swap();` on 512^3 TOTAL, uniform radius 2, 3 x float,
+    over this run's GPUs -- the timing loop of bin/bench_exchange.cu:39-54 (barrier, wall clock, trimean of 30, max
+    over ranks).  Beside it the UNMODIFIED reference library on the same box and GPUs (oracle/_ref/ref_exchange_uniform,
+    one process x N GPUs, its only mode here: no MPI in this image): its default transports (PeerAccessSender /
+    PeerCopySender: pack -> cudaMemcpyPeerAsync -> unpack) and Method::CudaMpi (tx_cuda_aware_mpi; the single-process
+    shim turns the device-pointer Isend/Irecv into a cudaMemcpyAsync, which favours the reference), and the same driver
+    source linked against OUR C++ library (bin/exchange_uniform) when bin/ was built."""
+    import torch
+    import torch.distributed as td
+
+    import stencil_b200 as sb
+
+    size, q, r = (512, 512, 512), 3, 2
+    dd = sb.DistributedDomain(*size)
+    dd.set_gpus(gpus)
+    dd.set_radius(sb.Radius.constant(r))
+    for _ in range(q):
+        dd.add_data(np.float32)
+    dd.realize()
+    host = td.new_group(backend="gloo") if world > 1 else None  # host-side barriers: no spinning NCCL kernel on the GPUs
+
+    def barrier():
+        if host is not None:
+            td.barrier(group=host)
+
+    times = []
+    for i in range(iters + 3):
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        dd.exchange()
+        dd.swap()
+        dt = time.perf_counter() - t0
+        if i >= 3:
+            times.append(dt)
+    t = torch.tensor(times, dtype=torch.float64, device="cuda")
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    times = t.cpu().numpy()
+    total = dd.exchange_bytes_for_method(sb.Method.Default)
+    peer = dd.exchange_bytes_for_method(sb.Method.CudaMemcpyPeer)
+    tb = torch.tensor([total, peer], dtype=torch.float64, device="cuda")
+    if world > 1:
+        td.all_reduce(tb)  # every rank counts what it sends
+    total, peer = float(tb[0]), float(tb[1])
+    dd.close()
+    us = trimean(times) * 1e6
+    out = {
+        "workload": "bench_exchange 512^3 total, uniform radius 2, 3 x float (BASELINE configs[2]); dd.exchange(); dd.swap(); trimean of %d, max over ranks" % iters,
+        "us": us,
+        "min_us": float(times.min()) * 1e6,
+        "bytes": int(total),
+        "cross_gpu_bytes": int(peer),
+        # payload every GPU sends (= receives) over NVLink per exchange / exchange time
+        "nvlink_gbs_per_dir": (peer / ngpu) / (us * 1e-6) / 1e9 if peer > 0 else 0.0,
+        "nvlink_peak_gbs_per_dir": 900.0,
+        "transport": "fused direct write into the neighbours' ghost cells (peer access / CUDA IPC), thin rows staged; ready/done flags on the device",
+    }
+    barrier()
+    if rank == 0:  # the reference library, one process x N GPUs, while the other ranks wait on the host
+        def ref(exe, how):
+            path = os.path.join(ROOT, exe)
+            if not os.path.exists(path):
+                return None
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=",".join(str(g) for g in range(ngpu)))
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE"):
+                env.pop(k, None)
+            try:
+                o = subprocess.run([path, "512", "512", "512", str(q), str(r), str(iters), how], cwd="/tmp", env=env, capture_output=True, text=True, timeout=300)
+                row = [ln for ln in o.stdout.splitlines() if "_exchange," in ln][-1].split(",")
+                return float(row[-2]) * 1e6  # trimean seconds -> us
+            except Exception as e:  # the reference aborting is a result, not a bench failure
+                return "failed: %s" % (str(e)[:80],)
+
+        out["reference_us"] = ref("oracle/_ref/ref_exchange_uniform", "default")
+        out["reference_cudampi_us"] = ref("oracle/_ref/ref_exchange_uniform", "cudampi")
+        out["ours_cpp_one_process_us"] = ref("bin/exchange_uniform", "default")
+        out["reference_note"] = "reference library unmodified, 1 process x %d GPU(s) (no MPI here); cudampi = Method::CudaMpi over the single-process shim" % ngpu
+    barrier()
+    return out
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -416,13 +446,15 @@ def run_ours(args, rank, world):
     # ---- CPU baseline (rank 0, N=1, bounded sample) -----------------------------------------
     cpu = None
     if rank == 0 and ngpu == 1 and not args.no_cpu_baseline:
-        r = time_cpu(n, dtype, steps=50, warmup=1, budget_s=12.0)
+        r = time_cpu(n, args.dtype, steps=50, warmup=1, budget_s=12.0)
         cpu = {
             "value": r["value"],
             "unit": UNIT,
             "cores": r["cores"],
             "kind": "port",
             "sample": f"{r['steps']} full iterations of {n}^3 {args.dtype} (<=12 s), oracle/stencil_oracle.c with OpenMP on {cpu_model()}",
+            "host": r["host"],
+            "omp": r["omp"],
         }
 
     if rank == 0:
@@ -460,9 +492,28 @@ def run_ours(args, rank, world):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
     jac.close()
     dd.close()
+    # ---- parity (outside every timed region): the same schedule on 128^3 per GPU against the single-address-space
+    # oracle, bit for bit, on every rank -- the analogue of the reference's whole-subdomain exchange check
+    # (test/test_cuda_mpi_exchange.cu:193-245) for the loop of bin/jacobi3d.cu:296-368
+    parity = None
+    if not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from jacobi_parity import check_jacobi_parity
+
+        kinds = {"fused": ("fused",) * 6 + ("queued",) * 2, "queued": ("queued",) * 6 + ("host-sync",) * 2, "host-sync": ("host-sync",) * 4}[schedule]
+        parity = check_jacobi_parity(scaled_size(128, 128, 128, ngpu), gpus, dtype, kinds, world)
+
+    xchg = None
+    if not args.no_exchange_bench:
+        xchg = halo_exchange_metric(rank, world, gpus, ngpu)
+    if rank == 0:
+        line["parity_check"] = parity
+        line["halo_exchange"] = xchg
+        print(json.dumps(line), flush=True)
+    if parity is not None and not parity["bit_exact"]:
+        raise SystemExit(f"bench.py: parity check FAILED: {parity}")
 
 
 def main():

@@ -179,6 +179,30 @@ typedef struct {
 } sb_halo_push;
 int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3],
                       const int64_t hi[3], const int64_t clo[3], const int64_t chi[3], const sb_halo_push *push, void *stream);
+/* The same launch with the ordering BETWEEN RANKS inside the kernel, replacing the reference's per-iteration host
+ * synchronisation (DistributedDomain::exchange() returns after MPI_Waitall / stream syncs, src/stencil.cu:1120-1186;
+ * bin/jacobi3d.cu:337-365) and this library's own sb_wait / sb_signal launches.  Only the CTAs on a face of the
+ * subdomain read ghost cells or write into a neighbour, so only they take part: before marching they poll
+ * wait_slots[i] (mailbox words in THIS GPU's memory, one per neighbour rank; ld.acquire.sys) until
+ * (int32)(*slot - wait_value) >= 0; after marching each fences its pushes and counts itself into *arrive, and the last
+ * one stores signal_value into signal_slots[i] (the neighbours' mailbox words for this rank, peer / IPC mapped;
+ * st.release.sys) and resets *arrive.  Protocol: iteration e waits for e and signals e + 1 -- a neighbour that has
+ * finished iteration e - 1 has (a) pushed the ghost values iteration e reads and (b) stopped reading the ghost cells
+ * iteration e overwrites.  order: 0 natural block order, 1 boundary CTAs dispatched first (the inner ~64 % of the CTAs
+ * then absorb the skew between ranks), 2 boundary CTAs last, -1 library default.  epoch (optional, device word): added
+ * to both values and incremented by the kernel, so a captured CUDA graph can be replayed.  sync == NULL: no handshake. */
+typedef struct {
+  const uint32_t *wait_slots[6];
+  uint32_t *signal_slots[6];
+  uint32_t *arrive; /* device word, zero before the first launch */
+  uint32_t *epoch;  /* device word or NULL */
+  int32_t n_wait, n_signal;
+  uint32_t wait_value, signal_value;
+  int32_t order;
+} sb_step_sync;
+int sb_jacobi3d_fused_sync(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3],
+                           const int64_t hi[3], const int64_t clo[3], const int64_t chi[3], const sb_halo_push *push,
+                           const sb_step_sync *sync, void *stream);
 /* init_kernel, bin/jacobi3d.cu:18-29: fill region with a constant */
 int sb_fill(sb_pitched dst, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3], const int64_t hi[3],
             double value, void *stream);

@@ -19,7 +19,7 @@ OBJ="$OUT/obj"
 mkdir -p "$OUT" "$OBJ"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 STAMP="$OUT/.built"
-if [ -f "$STAMP" ] && [ "$STAMP" -nt "$HERE/build_ref.sh" ] && [ "$STAMP" -nt "$HERE/ref_exchange_uniform.cu" ] && [ "$STAMP" -nt "$HERE/ref_astaroth_solve.cu" ] && [ "$STAMP" -nt "$REPO/src/mpi_shim.cpp" ] && [ -z "${FORCE:-}" ]; then
+if [ -f "$STAMP" ] && [ "$STAMP" -nt "$HERE/build_ref.sh" ] && [ "$STAMP" -nt "$HERE/ref_exchange_uniform.cu" ] && [ "$STAMP" -nt "$HERE/ref_astaroth_solve.cu" ] && [ "$STAMP" -nt "$HERE/ref_jacobi_golden.cu" ] && [ "$STAMP" -nt "$REPO/src/mpi_shim.cpp" ] && [ -z "${FORCE:-}" ]; then
   echo "oracle/_ref up to date"; exit 0
 fi
 DEFS="-DSTENCIL_USE_MPI=1 -DSTENCIL_USE_CUDA=1 -DSTENCIL_USE_CUDA_AWARE_MPI=1 -DSTENCIL_USE_CUDA_GRAPH=1 -DSTENCIL_SETUP_STATS=1 -DSTENCIL_OUTPUT_LEVEL=2 -DNDEBUG -DCATCH_CONFIG_NO_POSIX_SIGNALS"
@@ -48,6 +48,15 @@ done
 # our own baseline driver over the reference library (uniform radii only, see the file header)
 compile "$HERE/ref_exchange_uniform.cu" "$OBJ/ref_exchange_uniform.o"
 $NVCC $LINK -o "$OUT/ref_exchange_uniform" "$OBJ/ref_exchange_uniform.o" "$OBJ/bin_statistics.o" "${LIBOBJS[@]}" "$OBJ/mpi_shim.o"
+# golden-vector generator for the jacobi numerics: the reference driver's own kernels (bin/jacobi3d.cu, main renamed),
+# once with the reference's --use_fast_math (bin/CMakeLists.txt:56) and once with IEEE division
+for flavour in "" "_ieee"; do
+  o="$OBJ/ref_jacobi_golden$flavour.o"
+  if [ ! -f "$o" ] || [ "$HERE/ref_jacobi_golden.cu" -nt "$o" ]; then
+    $NVCC $FLAGS $([ -z "$flavour" ] && echo --use_fast_math) -c "$HERE/ref_jacobi_golden.cu" -o "$o"
+  fi
+  $NVCC $LINK -o "$OUT/ref_jacobi_golden$flavour" "$o" "$OBJ/bin_statistics.o" "${LIBOBJS[@]}" "$OBJ/mpi_shim.o"
+done
 # the reference's astaroth driver against the reference library (+ its config file, data only)
 AFLAGS="${FLAGS/-I$REF\/bin/} --use_fast_math -I$REF/astaroth -DAC_DEFAULT_CONFIG=\"oracle/_ref/astaroth.conf\""
 pids=()

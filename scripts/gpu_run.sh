@@ -1,0 +1,83 @@
+#!/bin/bash
+# One parameterised GPU script (replaces the per-experiment gpu_round*/gpu_multi* files of round 1).
+#   gpurun --timeout 900 -- 'bash scripts/gpu_run.sh <stage> [<stage> ...]'
+# Every stage writes under gpurun_out/<tag>/ (tag = $SB_TAG or "run") and prints a short summary.
+set -u
+TAG=${SB_TAG:-run}
+F=gpurun_out/$TAG
+mkdir -p "$F"
+N=${SB_NGPU:-1}
+PORT=29871
+
+pick() { # one summary line from a bench JSON line on stdin
+  grep "^{" | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline())
+r=d.get('roofline') or {}
+pc=d.get('parity_check') or {}
+hx=d.get('halo_exchange')
+if hx: print('  halo_exchange us %.1f' % hx['us'], 'ref', hx.get('reference_us'), 'ref_cudampi', hx.get('reference_cudampi_us'), 'ours_cpp', hx.get('ours_cpp_one_process_us'), 'nvlink GB/s/dir %.1f' % hx['nvlink_gbs_per_dir'])
+print('$1', 'n', d['n_gpus'], 'ms/step %.4f' % d['ms_per_step'], 'kernel %.4f' % r.get('kernel_ms', 0), 'frac %.3f' % r.get('step_frac_of_roofline', 0), 'per_gpu %.4g' % d['per_gpu'], 'launches', d['gpu_launches'], d['config']['schedule'], 'parity', pc.get('bit_exact'), pc.get('schedule'))"
+}
+
+bench() { # bench <label> <extra args...>   (N ranks under torchrun when N > 1)
+  local label=$1; shift
+  if [ "$N" -gt 1 ]; then
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $PORT \
+      bench.py --gpus "$N" "$@" 2>"$F/bench_${label}.err" | tee "$F/bench_${label}.json" | pick "$label"
+    PORT=$((PORT + 1))
+  else
+    timeout 400 python bench.py "$@" 2>"$F/bench_${label}.err" | tee "$F/bench_${label}.json" | pick "$label"
+  fi
+  tail -3 "$F/bench_${label}.err" | cut -c1-300
+}
+
+for stage in "$@"; do
+  echo "=== stage $stage (N=$N)"
+  case $stage in
+  tests) # the whole GPU suite
+    timeout 1700 python -m pytest tests -q -m gpu -x 2>&1 | tail -8 | tee "$F/pytest_gpu.txt" ;;
+  tests_jacobi)
+    timeout 900 python -m pytest tests/test_gpu_jacobi.py -q -m gpu -x 2>&1 | tail -8 | tee "$F/pytest_jacobi.txt" ;;
+  tests_mp) # multi-rank parity (needs N >= 2)
+    timeout 900 python -m pytest tests/test_gpu_exchange.py -q -m gpu -x -k "one_process or multi_gpu" 2>&1 | tail -8 | tee "$F/pytest_mp.txt" ;;
+  mp_check) # the torchrun parity script itself, with its per-shape lines
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29861 tests/mp_exchange_check.py 2>"$F/mp_check.err" | tee "$F/mp_check.txt" | cut -c1-400
+    tail -5 "$F/mp_check.err" | cut -c1-400 ;;
+  smoke)
+    timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 | tee "$F/smoke.txt" ;;
+  bench) # the line the driver reads
+    bench default --steps 30 --warmup 5 ;;
+  bench_quick)
+    bench quick --steps 30 --warmup 5 --no-cpu-baseline --no-e2e ;;
+  bench_orders) # block order of the fused kernel: natural / boundary first / boundary last
+    for o in 0 1 2; do SB_FUSED_ORDER=$o bench "order$o" --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity; done ;;
+  bench_f32)
+    bench f32 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --dtype f32 ;;
+  bench_queued)
+    bench queued --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --schedule queued --no-parity ;;
+  bench_launchsync) # the round-1 handshake (separate wait / signal launches) for the before/after
+    SB_FUSED_INKERNEL=0 bench launchsync --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity ;;
+  bench_reference)
+    timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tee "$F/bench_reference.json" | cut -c1-400 ;;
+  launches) # every launch of the bench command, cold and serialised: compare SHARES
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file "$F/launches.csv" python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity >"$F/ncu_launches.log" 2>&1
+    tail -12 "$F/launches.csv" | cut -c1-200 ;;
+  ncu_fused)
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:jacobi_fused_kernel -s 4 -c 1 -o "$F/prof_jacobi_fused" -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity >"$F/ncu_full.log" 2>&1
+    tail -3 "$F/ncu_full.log" ;;
+  sanitize) # memcheck on the small fused cases
+    timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_jacobi.py -q -m gpu -x -k "block_orders and float64" 2>&1 | tail -15 | tee "$F/sanitize.txt" ;;
+  cpp) # the C++ API: the reference's own suites and drivers against our library
+    ( timeout 600 bin/test_cuda 2>&1 | tail -3 ) | tee "$F/test_cuda.txt"
+    ( timeout 300 bin/test_cpu 2>&1 | tail -3 ) | tee "$F/test_cpu.txt" ;;
+  golden) # reference-generated golden vectors (oracle/ref/*.py), written to gpurun_out/
+    timeout 300 python oracle/ref/make_jacobi_golden.py 2>&1 | tail -8 ;;
+  astaroth)
+    SKIP_CELL=1 timeout 300 python scripts/time_astaroth.py 256 f64 5 2>&1 | tail -6 | tee "$F/astaroth_f64.txt"
+    SKIP_CELL=1 timeout 300 python scripts/time_astaroth.py 256 f32 5 2>&1 | tail -6 | tee "$F/astaroth_f32.txt" ;;
+  *) # anything else: a script path with arguments in SB_ARGS
+    if [ -f "$stage" ]; then timeout 900 bash "$stage" 2>&1 | tail -40 | tee "$F/$(basename "$stage").txt"; else echo "unknown stage $stage"; fi ;;
+  esac
+done
+rm -f plan_*.txt gpurun_out/plan_*.txt

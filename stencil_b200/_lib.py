@@ -50,6 +50,22 @@ class HaloPush(C.Structure):
     _fields_ = [("nbr", Pitched * 6), ("nbr_zsize", C.c_int64 * 6), ("x_dense", C.c_int64 * 2), ("x_recv", C.c_void_p * 2)]
 
 
+class StepSync(C.Structure):
+    """sb_step_sync: the in-kernel handshake of sb_jacobi3d_fused_sync (mailbox slots of the neighbour ranks)."""
+
+    _fields_ = [
+        ("wait_slots", C.c_void_p * 6),
+        ("signal_slots", C.c_void_p * 6),
+        ("arrive", C.c_void_p),
+        ("epoch", C.c_void_p),
+        ("n_wait", C.c_int32),
+        ("n_signal", C.c_int32),
+        ("wait_value", C.c_uint32),
+        ("signal_value", C.c_uint32),
+        ("order", C.c_int32),
+    ]
+
+
 # every symbol include/stencil_b200.h declares: (restype, argtypes)
 _SIGS = {
     "sb_last_error": (C.c_char_p, []),
@@ -80,6 +96,7 @@ _SIGS = {
     "sb_jacobi3d_regions": (C.c_int, [Pitched, Pitched, C.c_int, I3, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), I3, I3, C.c_void_p]),
     "sb_astaroth_substep": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, I3, I3, I3, C.POINTER(AstarothParams), C.c_int, C.c_void_p]),
     "sb_jacobi3d_fused": (C.c_int, [Pitched, Pitched, C.c_int, I3, I3, I3, I3, I3, C.POINTER(HaloPush), C.c_void_p]),
+    "sb_jacobi3d_fused_sync": (C.c_int, [Pitched, Pitched, C.c_int, I3, I3, I3, I3, I3, C.POINTER(HaloPush), C.POINTER(StepSync), C.c_void_p]),
     "sb_fill": (C.c_int, [Pitched, C.c_int, I3, I3, I3, C.c_double, C.c_void_p]),
     "sb_sqdiff": (C.c_int, [Pitched, Pitched, C.c_int, I3, I3, I3, C.c_void_p, C.c_void_p]),
     "sb_device_count": (C.c_int, [C.POINTER(C.c_int)]),

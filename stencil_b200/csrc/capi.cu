@@ -765,7 +765,34 @@ int sb_jacobi3d(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t ac
 
 int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3], const int64_t hi[3],
                       const int64_t clo[3], const int64_t chi[3], const sb_halo_push *push, void *stream) {
+  return sb_jacobi3d_fused_sync(dst, src, dtype_size, acc_origin, lo, hi, clo, chi, push, nullptr, stream);
+}
+
+int sb_jacobi3d_fused_sync(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3], const int64_t hi[3],
+                           const int64_t clo[3], const int64_t chi[3], const sb_halo_push *push, const sb_step_sync *sync, void *stream) {
   if (!push) return fail(SB_ERR_INVALID, "null push table");
+  sb::FusedSync fs{};
+  fs.order = -1;
+  if (sync) {
+    if (sync->n_wait < 0 || sync->n_wait > 6 || sync->n_signal < 0 || sync->n_signal > 6)
+      return fail(SB_ERR_INVALID, "between 0 and 6 neighbour slots per direction of the handshake");
+    if (sync->n_signal > 0 && !sync->arrive) return fail(SB_ERR_INVALID, "signalling needs the arrive counter");
+    for (int i = 0; i < sync->n_wait; ++i) {
+      if (!sync->wait_slots[i]) return fail(SB_ERR_INVALID, "null wait slot %d", i);
+      fs.wait_slot[i] = sync->wait_slots[i];
+    }
+    for (int i = 0; i < sync->n_signal; ++i) {
+      if (!sync->signal_slots[i]) return fail(SB_ERR_INVALID, "null signal slot %d", i);
+      fs.signal_slot[i] = sync->signal_slots[i];
+    }
+    fs.n_wait = sync->n_wait;
+    fs.n_signal = sync->n_signal;
+    fs.wait_value = sync->wait_value;
+    fs.signal_value = sync->signal_value;
+    fs.arrive = sync->arrive;
+    fs.epoch = sync->epoch;
+    fs.order = sync->order;
+  }
   sb::JacobiParams p{};
   int rc = to_alloc_box(src, dtype_size, acc_origin, lo, hi, p.lo, p.hi);
   if (rc != SB_OK) return rc;
@@ -814,9 +841,9 @@ int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int6
   // opposite face of src in place (x: the edge lane's scalar, y: the row above / below a strip).  With alternating row
   // phases (FP32 rows not a multiple of 16 bytes) the wrapped row must have the parity of the ghost row it replaces.
   auto self = [&](int d) { return push->nbr[d].ptr == dst.ptr && push->nbr[d].pitch == dst.pitch && push->nbr[d].ysize == dst.ysize; };
-  if (self(0) && self(1)) p.xwrap = 1; // a request: launch_jacobi_push keeps the x pushes when the vector layout rules it out
+  if (self(0) && self(1)) p.xwrap = 1; // a request: launch_jacobi_fused keeps the x pushes when the vector layout rules it out
   if (self(2) && self(3) && (src.pitch % 16 == 0 || (p.hi[1] - p.lo[1]) % 2 == 0)) p.ywrap = 1, p.push_ptr[2] = p.push_ptr[3] = nullptr;
-  const int n = sb::launch_jacobi_push(p, dtype_size, static_cast<cudaStream_t>(stream));
+  const int n = sb::launch_jacobi_fused(p, fs, dtype_size, static_cast<cudaStream_t>(stream));
   if (n < 0) return fail(SB_ERR_INVALID, "dense x faces need a 16-byte aligned first compute cell, whole warp strips along x and z chunks of <= 32 planes");
   g_launches += uint64_t(n);
   SB_CUDA(cudaGetLastError());

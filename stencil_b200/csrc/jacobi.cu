@@ -74,21 +74,14 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // per step, taken by two lanes per row), y and z faces by an epilogue over the few warps that own them.
 // The halo exchange of the next iteration is thereby part of this kernel: no pack / unpack pass over the 8-byte-wide
 // x faces, no separate exterior kernel.
-template <typename T, int VX, int RY, int MB, bool SHIFT, int PUSH = 0> // PUSH: 0 plain, 1 fused halo push, 2 fused without x pushes, 3 fused with dense x faces
-__global__ void __launch_bounds__(256, MB)
-    jacobi_march_kernel(const __grid_constant__ JacobiParams p, int tiles_x, int tiles_y) {
+template <typename T, int VX, int RY, bool SHIFT, int PUSH> // PUSH: 0 plain, 1 fused halo push, 2 fused without x pushes, 3 fused with dense x faces
+__device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, const int by, const int bz) {
   static_assert(!SHIFT || (RY == 1 && VX >= 2), "the phase-shifted variant handles one row per warp");
   static_assert(!PUSH || RY == 1, "the push variant handles one row per warp");
   using V = Vec<T, VX>;
   constexpr int WY = 8; // warps stacked in y
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-
-  int b = blockIdx.x;
-  const int bx = b % tiles_x;
-  b /= tiles_x;
-  const int by = b % tiles_y;
-  const int bz = b / tiles_y;
 
   const long long S = p.slice, P = p.pitch;
   const int y = p.lo[1] + (by * WY + warp) * RY;         // first row of this warp
@@ -188,6 +181,22 @@ __global__ void __launch_bounds__(256, MB)
     if (xside >= 0) xpush = true;
   }
 
+  // PUSH, y faces: the warp that owns the first (last) row of the subdomain stores it a second time, into the ghost row
+  // of the -y (+y) neighbour, with the same loop-invariant address difference (needs the neighbour's plane size to equal
+  // ours -- always true on a grid partition with equal x / y extents; otherwise the epilogue below does it).  Warp-uniform.
+  long long ydiff = 0;
+  bool ypush = false, yvec = false;
+  int ydir = -1;
+  if (PUSH && row_ok[0]) {
+    ydir = (y == p.lo[1]) ? 2 : ((y == p.hi[1] - 1) ? 3 : -1);
+    if (ydir == 2 && y == p.hi[1] - 1 && !p.push_ptr[2]) ydir = 3; // one-row subdomain: the loop serves one side
+    if (ydir >= 0 && p.push_ptr[ydir] && p.push_slice[ydir] == S) {
+      ydiff = (p.push_ptr[ydir] + (long long)x * (long long)sizeof(T) + (long long)z0 * S) - pw[0];
+      ypush = true;
+      yvec = ((unsigned long long)(pw[0] + ydiff) % sizeof(V)) == 0;
+    }
+  }
+
   V A[RY], B[RY], C[RY];
 #pragma unroll
   for (int j = 0; j < RY; ++j) {
@@ -261,6 +270,17 @@ __global__ void __launch_bounds__(256, MB)
             if (cell_ok & (1u << i)) reinterpret_cast<T *>(pw[j])[i] = out.v[i];
         }
       }
+      if (PUSH) {
+        if (ypush) { // one warp in 512 rows
+          if (full && yvec) {
+            *reinterpret_cast<V *>(pw[j] + ydiff) = out;
+          } else {
+#pragma unroll
+            for (int i = 0; i < VX; ++i)
+              if (cell_ok & (1u << i)) reinterpret_cast<T *>(pw[j] + ydiff)[i] = out.v[i];
+          }
+        }
+      }
       if (PUSH == 3) {
         if (xpush) xstage[xside][warp][z - z0] = (xside == 0) ? out.v[0] : out.v[VX - 1];
       }
@@ -303,13 +323,15 @@ __global__ void __launch_bounds__(256, MB)
     }
   }
   if (PUSH) {
-    // y and z faces, after the loop: every lane re-reads the face cells IT stored in this chunk (its own writes: no
-    // barrier, L2-resident) and stores them into the ghost row / plane of the neighbour.  Only the two edge rows of the
-    // subdomain (2 of 512 warps-rows) and the first / last chunk take these paths.
+    // Faces not served by the loop, after it: every lane re-reads the face cells IT stored in this chunk (its own
+    // writes: no barrier, L2-resident) and stores them into the ghost row / plane of the neighbour.  y: only a row
+    // whose neighbour has another plane size, or the second side of a one-row subdomain; z: the first / last chunk.
     if (!row_ok[0] || !cell_ok) return;
     const char *mine = p.dst + (long long)y * P + (long long)x * (long long)sizeof(T);
-    const int dy = (y == p.lo[1]) ? 2 : ((y == p.hi[1] - 1) ? 3 : -1);
-    if (dy >= 0 && p.push_ptr[dy]) {
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const int dy = 2 + side;
+      if (!(side == 0 ? y == p.lo[1] : y == p.hi[1] - 1) || !p.push_ptr[dy] || (ypush && ydir == dy)) continue;
       char *tgt = p.push_ptr[dy] + (long long)x * (long long)sizeof(T);
 #pragma unroll 8
       for (int zz = z0; zz < z1; ++zz) {
@@ -322,14 +344,119 @@ __global__ void __launch_bounds__(256, MB)
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
       const bool on = side == 0 ? (z0 == p.lo[2]) : (z1 == p.hi[2]);
-      char *tgt = p.push_ptr[4 + side];
-      if (!on || !tgt) continue;
+      if (!on || !p.push_ptr[4 + side]) continue;
       const int zz = side == 0 ? z0 : z1 - 1;
-      const T *r = reinterpret_cast<const T *>(mine + (long long)zz * S);
+      char *tgt = p.push_ptr[4 + side] + (long long)y * p.push_pitch[4 + side] + (long long)x * (long long)sizeof(T);
+      const char *r = mine + (long long)zz * S;
+      if (full && ((unsigned long long)tgt % sizeof(V)) == 0 && ((unsigned long long)r % sizeof(V)) == 0) {
+        *reinterpret_cast<V *>(tgt) = *reinterpret_cast<const V *>(r);
+      } else {
 #pragma unroll
-      for (int i = 0; i < VX; ++i) {
-        if (cell_ok & (1u << i))
-          *reinterpret_cast<T *>(tgt + (long long)y * p.push_pitch[4 + side] + (long long)(x + i) * (long long)sizeof(T)) = r[i];
+        for (int i = 0; i < VX; ++i)
+          if (cell_ok & (1u << i)) reinterpret_cast<T *>(tgt)[i] = reinterpret_cast<const T *>(r)[i];
+      }
+    }
+  }
+}
+
+template <typename T, int VX, int RY, int MB, bool SHIFT>
+__global__ void __launch_bounds__(256, MB) jacobi_march_kernel(const __grid_constant__ JacobiParams p, int tiles_x, int tiles_y) {
+  int b = blockIdx.x;
+  const int bx = b % tiles_x;
+  b /= tiles_x;
+  march_body<T, VX, RY, SHIFT, 0>(p, bx, b % tiles_y, b / tiles_y);
+}
+
+// Fused iteration (launch_jacobi_fused): the march over the WHOLE compute region with the halo exchange of the next
+// iteration and the ordering between ranks inside the kernel.
+//  * CTAs that touch no face of the subdomain ("inner": 64 % of them at 512^3) run the plain loop (PUSH = 0); the
+//    boundary CTAs run the push variant.  One kernel, one CTA-uniform branch.
+//  * order 1 / 2: the block index is remapped so that all boundary CTAs are dispatched first / last.  Boundary CTAs are
+//    the only ones that read ghost cells and the only ones that write into a neighbour, so they alone take part in the
+//    handshake: before the march a boundary CTA polls the mailbox slots of the neighbour ranks (ld.acquire.sys) until
+//    each has finished the previous iteration (its pushes have landed in my ghost cells AND it no longer reads the ghost
+//    cells I am about to overwrite); after the march it fences and counts itself in, and the last one to arrive stores
+//    the new iteration number into the neighbours' mailboxes (st.release.sys).  The inner CTAs (~230 us of work) absorb
+//    the skew between ranks, so no rank ever idles behind a separate wait / signal launch.
+template <typename T, int VX, bool SHIFT, int XM>
+__global__ void __launch_bounds__(256, 4)
+    jacobi_fused_kernel(const __grid_constant__ JacobiParams p, const __grid_constant__ FusedSync s, int nx, int ny, int nz) {
+  // boundary tiles: the first and the last along every axis (phase-shifted rows end one strip later than the others, so
+  // with SHIFT the last TWO strips along x may hold cells of the +x face)
+  const int xcols = min(nx, SHIFT ? 3 : 2), yrows = min(ny, 2), zslabs = min(nz, 2);
+  const int ix = nx - xcols, iy = ny - yrows, iz = nz - zslabs;
+  const int inner = ix * iy * iz;
+  int b = blockIdx.x;
+  int bx, by, bz;
+  bool edge;
+  if (s.order == 0) {
+    bx = b % nx;
+    b /= nx;
+    by = b % ny;
+    bz = b / ny;
+    edge = bx == 0 || bx >= nx - (xcols - 1) || by == 0 || by == ny - 1 || bz == 0 || bz == nz - 1;
+  } else {
+    const int nedge = nx * ny * nz - inner;
+    edge = s.order == 1 ? b < nedge : b >= inner;
+    if (!edge) {
+      const int j = s.order == 1 ? b - nedge : b;
+      bx = 1 + j % ix;
+      by = 1 + (j / ix) % iy;
+      bz = 1 + j / (ix * iy);
+    } else {
+      int k = s.order == 1 ? b : b - inner;
+      const int slab = nx * ny;
+      if (k < slab * zslabs) { // the -z slab, then the +z slab
+        bz = (k < slab) ? 0 : nz - 1;
+        k %= slab;
+        bx = k % nx;
+        by = k / nx;
+      } else { // rim of a middle plane: the -y row, the +y row, then the boundary strips of every middle row
+        k -= slab * zslabs;
+        const int rim = nx * yrows + iy * xcols;
+        bz = 1 + k / rim;
+        int r = k % rim;
+        if (r < nx * yrows) {
+          by = (r < nx) ? 0 : ny - 1;
+          bx = r % nx;
+        } else {
+          r -= nx * yrows;
+          by = 1 + r / xcols;
+          const int c = r % xcols;
+          bx = (c == 0) ? 0 : nx - xcols + c;
+        }
+      }
+    }
+  }
+  if (!edge) {
+    march_body<T, VX, 1, SHIFT, 0>(p, bx, by, bz);
+    return;
+  }
+  uint32_t epoch = 0;
+  if (s.n_wait > 0 || s.n_signal > 0) {
+    if (s.epoch) epoch = *reinterpret_cast<const volatile uint32_t *>(s.epoch);
+    if ((int)threadIdx.x < s.n_wait) {
+      const uint32_t want = s.wait_value + epoch;
+      uint32_t v;
+      while (true) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(s.wait_slot[threadIdx.x]) : "memory");
+        if ((int32_t)(v - want) >= 0) break; // wrap-safe "v >= want"
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+  }
+  march_body<T, VX, 1, SHIFT, XM>(p, bx, by, bz);
+  if (s.n_signal > 0) {
+    __syncthreads(); // every thread's pushes are issued ...
+    if (threadIdx.x == 0) {
+      __threadfence_system(); // ... and performed system-wide before this CTA counts itself in
+      if (atomicAdd(s.arrive, 1u) == (unsigned)(nx * ny * nz - inner) - 1u) {
+        __threadfence_system();
+        *s.arrive = 0; // the next launch starts from zero (stream order)
+        if (s.epoch) *s.epoch = epoch + 1;
+        const uint32_t value = s.signal_value + epoch;
+        for (int i = 0; i < s.n_signal; ++i) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.signal_slot[i]), "r"(value) : "memory");
       }
     }
   }
@@ -462,7 +589,7 @@ __global__ void __launch_bounds__(256) sqdiff_kernel(const char *a, const char *
 
 int env_int(const char *name, int dflt);
 
-template <typename T, int VX, bool SHIFT> int launch_march_push(const JacobiParams &p, cudaStream_t stream) {
+template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p, const FusedSync &s, cudaStream_t stream) {
   const int x0a = p.x0a;
   const int tiles_x = (p.hi[0] - x0a + (SHIFT ? VX / 2 : 0) + 32 * VX - 1) / (32 * VX);
   const int ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
@@ -470,11 +597,11 @@ template <typename T, int VX, bool SHIFT> int launch_march_push(const JacobiPara
   const int tiles_y = (ny + 7) / 8;
   const long long blocks = (long long)tiles_x * tiles_y * tiles_z;
   if (p.xdense[0] || p.xdense[1] || p.xghost_ptr[0] || p.xghost_ptr[1])
-    jacobi_march_kernel<T, VX, 1, 4, SHIFT, 3><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
+    jacobi_fused_kernel<T, VX, SHIFT, 3><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
   else if (p.push_ptr[0] || p.push_ptr[1])
-    jacobi_march_kernel<T, VX, 1, 4, SHIFT, 1><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
-  else // no x face to push (periodic self-neighbour read in place, or nothing asked): the loop is the plain kernel's
-    jacobi_march_kernel<T, VX, 1, 4, SHIFT, 2><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
+    jacobi_fused_kernel<T, VX, SHIFT, 1><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
+  else // no x face to push (periodic self-neighbour read in place, or nothing asked)
+    jacobi_fused_kernel<T, VX, SHIFT, 2><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
   return 1;
 }
 
@@ -614,7 +741,7 @@ static int pick_vectors(JacobiParams &p, int dtype_size, bool allow_shift, bool 
   return origin(1, 0);
 }
 
-int launch_jacobi_push(const JacobiParams &p_in, int dtype_size, cudaStream_t stream) {
+int launch_jacobi_fused(const JacobiParams &p_in, const FusedSync &sync_in, int dtype_size, cudaStream_t stream) {
   JacobiParams p = p_in;
   const int ex = p.hi[0] - p.lo[0], ey = p.hi[1] - p.lo[1], ez = p.hi[2] - p.lo[2];
   if (ex <= 0 || ey <= 0 || ez <= 0) return 0;
@@ -624,6 +751,11 @@ int launch_jacobi_push(const JacobiParams &p_in, int dtype_size, cudaStream_t st
   p.zchunk = zchunk_env > 0 ? zchunk_env : 32;
   if (p.zchunk > ez) p.zchunk = ez;
   p.prefetch = pf;
+  FusedSync sync = sync_in;
+  if (sync.order < 0 || sync.order > 2) { // default: boundary CTAs first when ranks are ordered inside the kernel, natural order otherwise
+    const int order_env = env_int("SB_FUSED_ORDER", -1); // read per launch: tests switch it
+    sync.order = (order_env >= 0 && order_env <= 2) ? order_env : ((sync.n_wait > 0 || sync.n_signal > 0) ? 1 : 0);
+  }
   bool shift = false;
   const int vx = pick_vectors(p, dtype_size, allow_shift != 0, &shift);
   // x wrap (periodic self-neighbour read in place) works through the edge lanes' scalar load, so the first compute cell
@@ -636,12 +768,12 @@ int launch_jacobi_push(const JacobiParams &p_in, int dtype_size, cudaStream_t st
     if (shift || p.x0a != p.lo[0] || (p.hi[0] - p.lo[0]) % (32 * vx) != 0 || p.zchunk > 32) return -1;
   }
   if (dtype_size == 8) {
-    if (vx == 2) return shift ? launch_march_push<double, 2, true>(p, stream) : launch_march_push<double, 2, false>(p, stream);
-    return launch_march_push<double, 1, false>(p, stream);
+    if (vx == 2) return shift ? launch_fused<double, 2, true>(p, sync, stream) : launch_fused<double, 2, false>(p, sync, stream);
+    return launch_fused<double, 1, false>(p, sync, stream);
   }
-  if (vx == 4) return shift ? launch_march_push<float, 4, true>(p, stream) : launch_march_push<float, 4, false>(p, stream);
-  if (vx == 2) return launch_march_push<float, 2, false>(p, stream);
-  return launch_march_push<float, 1, false>(p, stream);
+  if (vx == 4) return shift ? launch_fused<float, 4, true>(p, sync, stream) : launch_fused<float, 4, false>(p, sync, stream);
+  if (vx == 2) return launch_fused<float, 2, false>(p, sync, stream);
+  return launch_fused<float, 1, false>(p, sync, stream);
 }
 
 int launch_fill(char *dst, long long pitch, long long slice, const int lo[3], const int hi[3], int dtype_size, double value,

@@ -44,6 +44,17 @@ struct JacobiParams {
   long long xghost_pitch[2];
 };
 
+// Ordering between ranks inside the fused kernel (see jacobi_fused_kernel).  All pointers are device addresses.
+struct FusedSync {
+  const uint32_t *wait_slot[6]; // local mailbox slots, one per neighbour rank: proceed when (int32)(*slot - wait_value) >= 0
+  uint32_t *signal_slot[6];     // the neighbours' slots for this rank (peer / IPC mapped)
+  uint32_t *arrive;             // boundary-CTA counter (device, zero before the first launch; the kernel resets it)
+  uint32_t *epoch;              // optional device word added to both values and incremented by the kernel (graph replay)
+  int n_wait, n_signal;
+  uint32_t wait_value, signal_value;
+  int order; // 0 natural block order, 1 boundary CTAs first, 2 boundary CTAs last, -1 default
+};
+
 // Up to 8 thin regions (the exterior slabs of one subdomain) updated by ONE launch.
 struct JacobiRegions {
   int n;
@@ -57,7 +68,7 @@ int launch_jacobi_regions(const JacobiParams &p, const JacobiRegions &r, int dty
 int launch_jacobi(const JacobiParams &p, int dtype_size, cudaStream_t stream);
 // the same update over the WHOLE compute region [lo, hi) of a subdomain; every boundary cell is also stored into the
 // ghost cell of the face neighbour that needs it (p.push_*), so the next iteration needs no halo exchange
-int launch_jacobi_push(const JacobiParams &p, int dtype_size, cudaStream_t stream);
+int launch_jacobi_fused(const JacobiParams &p, const FusedSync &sync, int dtype_size, cudaStream_t stream);
 int launch_fill(char *dst, long long pitch, long long slice, const int lo[3], const int hi[3], int dtype_size, double value,
                 cudaStream_t stream);
 int launch_sqdiff(const char *a, const char *b, long long pitch, long long slice, const int lo[3], const int hi[3],

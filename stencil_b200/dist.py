@@ -132,6 +132,15 @@ class RemoteDomains:
         self._done_local = [self.flags + 4 * (n + b) for b in self.nbrs]
         self._step_remote = (C.c_void_p * max(k, 1))(*[self.peer_flags[b] + 4 * (2 * n + w.rank) for b in self.nbrs])
         self._step_local = [self.flags + 4 * (2 * n + b) for b in self.nbrs]
+        # iteration counter of the fused jacobi schedule: lives with the mailboxes (not with a Jacobi3D object) so that
+        # the values only ever grow; every rank advances it in lockstep (one per fused iteration)
+        self.step_epoch = 0
+
+    def step_slots(self, ranks):
+        """(slots in MY mailbox written by `ranks`, my slot in each of their mailboxes) for the in-kernel handshake of
+        sb_jacobi3d_fused_sync."""
+        n, me = self.w.size, self.w.rank
+        return [self.flags + 4 * (2 * n + b) for b in ranks], [self.peer_flags[b] + 4 * (2 * n + me) for b in ranks]
 
     def pitched(self, idx: Vec, q: int, parity: int) -> Tuple[Pitched, int]:
         dom = self.remote[tuple(idx)]

@@ -46,8 +46,7 @@ def fused_x_mode(part, owner, elem_size: int, radius: Radius, mode: str = "") ->
     "direct": no x face crosses ranks -- the kernel stores boundary cells into the neighbour's ghost cells (own memory or
               a peer GPU of this process) or reads a periodic self-neighbour in place;
     "dense":  x faces cross ranks and travel as 256-byte lines into dense receive arrays (kernel mode 3): needs whole warp
-              strips along x and rows of one 16-byte phase; chosen by default only where it was validated and measured
-              faster this round (z faces inside a rank: 2 and 4 ranks), always with mode "1", never with mode "0";
+              strips along x and rows of one 16-byte phase (mode "0" = SB_FUSED_IPC=0 switches it off);
     "queued": fall back to the queued schedule (Jacobi3D.step_async)."""
     from .domain import get_neighbor
 
@@ -61,8 +60,22 @@ def fused_x_mode(part, owner, elem_size: int, radius: Radius, mode: str = "") ->
         part.subdomain_size(i)[0] % strip == 0 and ((part.subdomain_size(i)[0] + radius.x(-1) + radius.x(1)) * elem_size) % 16 == 0
         for i in part.indices()
     )
-    want = mode == "1" or (mode == "" and not crosses(FACE_DIRS[4:]))
-    return "dense" if (want and layout and mode != "0") else "queued"
+    return "dense" if (layout and mode != "0") else "queued"
+
+
+def fused_schedule(dd, elem_size: int, mode: str = "") -> str:
+    """Which schedule Jacobi3D.step_fused runs -- "fused" or "queued" -- as a pure function of the GLOBAL partition,
+    radius and transport, so that every rank takes the same one (a rank on another schedule would wait on flags the
+    others never write)."""
+    r = dd.radius_
+    if any(r.dir(d6) != 1 for d6 in FACE_DIRS):
+        return "queued"  # the fused kernel pushes face radius 1 (bin/jacobi3d.cu:237-246)
+    if getattr(dd, "_use_nccl", False):
+        return "queued"  # it stores into peer memory: not available on the NCCL fallback
+    part = dd.partition_
+    if any(part.subdomain_size(i)[0] < 16 for i in part.indices()):
+        return "queued"
+    return "queued" if fused_x_mode(part, dd._owner, elem_size, r, mode) == "queued" else "fused"
 
 
 class Jacobi3D:
@@ -238,11 +251,6 @@ class Jacobi3D:
 
         dd, h = self.dd, self.h
         r = dd.radius_
-        for d6 in ((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)):
-            if r.dir(d6) != 1:
-                raise RuntimeError("the fused jacobi schedule needs face radius 1 (bin/jacobi3d.cu:237-246)")
-        if getattr(dd, "_use_nccl", False):
-            raise RuntimeError("the fused jacobi schedule stores into peer memory: not available on the NCCL fallback")
         dirs = ((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1))
         # An x face is one 8-byte cell per row.  Pushed cell by cell into another GPU it costs 17 us per iteration through
         # in-process peer access (fine) but 78 us through CUDA-IPC mappings; shipping a dense copy between kernels, or
@@ -262,8 +270,8 @@ class Jacobi3D:
             from . import dist as _dist
 
             dense = all(_dist.all_gather_object(bool(dense)))
-        if x_crosses_ranks and not dense:
-            raise RuntimeError("x faces cross ranks and the dense x path does not apply: the queued schedule is the faster one")
+        if x_crosses_ranks and not dense:  # the same on every rank (all-gathered)
+            return False
         self._xbuf, self._xopened = [], []
         recv, remote_recv = {}, {}
         L = lib()
@@ -364,10 +372,35 @@ class Jacobi3D:
                     self._fused_nbr_slots.append(sorted(slots))
             self._fused_calls.append(per_dom)
             self._init_plans.append(inits)
-        self._fn_fused = lib().sb_jacobi3d_fused
+        self._fn_fused = lib().sb_jacobi3d_fused_sync
         self._fused_epoch = 0
         self._ev_fused = None
         self._ghosts_current = False
+        # Ordering between ranks.  One subdomain per rank (the torchrun layout): inside the kernel -- its boundary CTAs
+        # poll the face-neighbour ranks' counters and the last one signals (sb_jacobi3d_fused_sync); no extra launch.
+        # Several subdomains per rank: one counter per rank, signalled by a tiny kernel after all of them (sb_signal).
+        self._sync = None
+        if dd._remote is not None and len(dd.domains()) == 1 and os.environ.get("SB_FUSED_INKERNEL", "1") != "0":
+            idx = tuple(dd.domain_idx_[0])
+            ranks = sorted({dd._owner[tuple(get_neighbor(idx, dv, part.dim))][0] for dv in dirs} - {dd._world.rank})
+            if ranks:
+                from ._lib import StepSync
+
+                parr = C.c_void_p()
+                check(L.sb_malloc(C.byref(parr), 4, dd.domains()[0].gpu()))
+                check(L.sb_memset(parr, 0, 4, dd.domains()[0].gpu(), None))
+                check(L.sb_device_sync(dd.domains()[0].gpu()))
+                self._arrive = int(parr.value)
+                mine, theirs = dd._remote.step_slots(ranks)
+                sy = StepSync()
+                for i, (a, b) in enumerate(zip(mine, theirs)):
+                    sy.wait_slots[i], sy.signal_slots[i] = a, b
+                sy.n_wait = sy.n_signal = len(ranks)
+                sy.arrive = self._arrive
+                sy.epoch = None
+                sy.order = int(os.environ.get("SB_FUSED_ORDER", "-1"))
+                self._sync = sy
+        return True
 
     def step_fused(self, timing=None) -> None:
         """One iteration as ONE kernel per subdomain: the jacobi update of the whole compute region, with every boundary
@@ -381,12 +414,13 @@ class Jacobi3D:
         import torch
 
         if not hasattr(self, "_fused_calls"):
-            try:
-                self._build_fused()
-                self.fused_supported = all(d.size()[0] >= 16 for d in self.dd.domains())
-            except RuntimeError:
-                self._fused_calls, self.fused_supported = [], False
-        if not self.fused_supported:  # see _build_fused: the queued schedule computes the same iteration
+            import os
+
+            es = self.dd.domains()[0].elem_size(self.h.id)
+            self._fused_calls = []
+            # a pure function of the global partition; _build_fused adds one all-gathered layout check (the same everywhere)
+            self.fused_supported = fused_schedule(self.dd, es, os.environ.get("SB_FUSED_IPC", "")) == "fused" and self._build_fused()
+        if not self.fused_supported:  # the queued schedule computes the same iteration
             return self.step_async(timing=timing)
         dd = self.dd
         if self._ev_ext is not None:
@@ -418,11 +452,15 @@ class Jacobi3D:
                 for sj in self._fused_nbr_slots[di]:
                     if sj != di:
                         s.wait_event(prev[sj])
-            if remote is not None and self._fused_epoch > 0:
-                remote.wait_step(self._fused_epoch, s)
+            sync = self._sync
+            if sync is not None:  # iteration e waits for e and signals e + 1, inside the kernel
+                sync.wait_value = remote.step_epoch & 0xFFFFFFFF
+                sync.signal_value = (remote.step_epoch + 1) & 0xFFFFFFFF
+            elif remote is not None:
+                remote.wait_step(remote.step_epoch, s)
             if timing is not None and di == 0:
                 timing[0].record(s)
-            check(self._fn_fused(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], C.byref(a[8]), a[9]))
+            check(self._fn_fused(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], C.byref(a[8]), C.byref(sync) if sync is not None else None, a[9]))
             if timing is not None and di == 0:
                 timing[1].record(s)
             e = torch.cuda.Event()
@@ -430,17 +468,22 @@ class Jacobi3D:
             events.append(e)
         self._fused_epoch += 1
         if remote is not None:
-            # one counter per rank: signal after ALL local subdomains of this iteration are done
-            s0 = self.streams[0]
-            for e in events[1:]:
-                s0.wait_event(e)
-            remote.signal_step(self._fused_epoch, s0)
+            remote.step_epoch += 1
+            if self._sync is None:
+                # one counter per rank: signal after ALL local subdomains of this iteration are done
+                s0 = self.streams[0]
+                for e in events[1:]:
+                    s0.wait_event(e)
+                remote.signal_step(remote.step_epoch, s0)
         self._ev_fused = events
         dd.swap()
 
     def close(self) -> None:
         """Drain the queued work; release the dense x receive arrays of the SB_FUSED_IPC experiment."""
         self.synchronize()
+        if getattr(self, "_arrive", None):
+            lib().sb_free(C.c_void_p(self._arrive), self.dd.domains()[0].gpu())
+            self._arrive, self._sync = None, None
         if not getattr(self, "_xbuf", None) and not getattr(self, "_xopened", None):
             return
         import torch.distributed as td

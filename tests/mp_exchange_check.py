@@ -51,53 +51,25 @@ def main():
                     assert np.array_equal(got, want), (rank, size, rep, q)
             dd.swap()
         dd.close()
-    # jacobi through the multi-process path: 5 iterations, compare with a single-address-space oracle run
-    from oracle import c_oracle as co
-    from oracle import geometry as g
+    # jacobi through the multi-process path, compared with a single-address-space oracle run (tests/jacobi_parity.py).
+    # 64-cell multiples along x per rank = whole warp strips, so the fused schedule ships dense x columns between ranks.
+    # The global shapes make the partitioner cut x, then y, then z (and all of them with more ranks), so every face
+    # direction crosses ranks in some case.
+    from jacobi_parity import check_jacobi_parity
 
-    n = 128  # 64 cells along x per rank: whole warp strips, so the fused schedule ships dense x columns between ranks
-    dd = sb.DistributedDomain(n, n, n)
-    dd.set_gpus([local])
-    dd.set_radius(jacobi_radius())
-    h = dd.add_data(np.float64)
-    dd.realize()
-    jac = Jacobi3D(dd, h)
-    jac.init(0.5)
-    # two host-synchronised iterations, then three queued back to back (events + device-side flags only)
-    for _ in range(2):
-        jac.step()
     fused = os.environ.get("SB_FORCE_NCCL") != "1"  # the fused schedule stores into peer memory
-    for it in range(3):
-        if fused and it != 1:
-            jac.step_fused()  # update + halo push into the neighbour ranks' ghost cells, ordered by device-side counters
-        else:
-            jac.step_async()
-    jac.synchronize()
-    ro = g.Radius.face_edge_corner(1, 0, 0)
-    od = no.Domains((n, n, n), ro, [np.float64], n_subdomains=world)
-    nxt = {}
-    for i in od.indices:
-        od.arrays[i][0][...] = 0
-        no.box(od.arrays[i][0], (1, 1, 1), od.sizes[i])[...] = 0.5
-        nxt[i] = np.zeros_like(od.arrays[i][0])
-    creg = ((0, 0, 0), (n, n, n))
-    for _ in range(5):
-        for i in od.indices:
-            lo = od.origins[i]
-            hi = tuple(lo[a] + od.sizes[i][a] for a in range(3))
-            co.jacobi_region(nxt[i], od.arrays[i][0], g.accessor_origin(lo, ro), *g.get_interior(lo, hi, ro), *creg)
-        od.exchange()
-        for i in od.indices:
-            lo = od.origins[i]
-            hi = tuple(lo[a] + od.sizes[i][a] for a in range(3))
-            for elo, ehi in g.get_exterior(lo, hi, ro):
-                co.jacobi_region(nxt[i], od.arrays[i][0], g.accessor_origin(lo, ro), elo, ehi, *creg)
-            od.arrays[i][0], nxt[i] = nxt[i], od.arrays[i][0]
-    d = dd.domains()[0]
-    i = dd.domain_idx_[0]
-    got = d.quantity_to_host(0)
-    assert np.array_equal(no.box(got, (1, 1, 1), od.sizes[i]), no.box(od.arrays[i][0], (1, 1, 1), od.sizes[i])), rank
-    dd.close()
+    mixed = ("host-sync", "host-sync", "fused", "queued", "fused", "fused", "fused", "queued", "fused")
+    shapes = {
+        2: [(256, 128, 128), (128, 192, 128), (64, 128, 256)],  # cut along x / y / z
+        4: [(512, 128, 128), (256, 256, 128), (64, 256, 256)],  # (4,1,1), (2,2,1), (1,2,2)
+        8: [(256, 256, 256), (1024, 128, 128)],  # (2,2,2), (8,1,1)
+    }.get(world, [(128 * world, 128, 128)])
+    for size in shapes:
+        for dt in (np.float64, np.float32):
+            res = check_jacobi_parity(size, [local], dt, mixed if fused else ("host-sync", "queued", "queued"), world)
+            if rank == 0:
+                print("jacobi parity", res, flush=True)
+            assert res["bit_exact"], res
     td.barrier()
     if rank == 0:
         mode = "NCCL fallback" if os.environ.get("SB_FORCE_NCCL") == "1" else "CUDA-IPC direct write"

@@ -124,7 +124,7 @@ def test_neighbor_wrap_vs_reference():
 def test_fused_schedule_choice_per_partition():
     """Jacobi3D picks how x faces travel in the fused schedule from the partition and the ownership table alone (every
     rank evaluates the same function): direct pushes while x stays inside a rank, dense 256-byte lines across ranks where
-    the layout allows it and the combination was validated (z inside a rank), else the queued schedule."""
+    the layout allows it (also on 8 ranks, where y and z faces cross ranks too), else the queued schedule."""
     from stencil_b200.domain import Partition, Radius
     from stencil_b200.jacobi import fused_x_mode
 
@@ -144,8 +144,8 @@ def test_fused_schedule_choice_per_partition():
     assert tuple(four.dim) == (2, 2, 1) and fused_x_mode(four, owners(four, 1), 8, r) == "dense"
     eight = Partition((1024, 1024, 1024), r, 1, 8)
     assert tuple(eight.dim) == (2, 2, 2)
-    assert fused_x_mode(eight, owners(eight, 1), 8, r) == "queued"  # z crosses ranks: not validated this round
-    assert fused_x_mode(eight, owners(eight, 1), 8, r, "1") == "dense"
+    assert fused_x_mode(eight, owners(eight, 1), 8, r) == "dense"
+    assert fused_x_mode(eight, owners(eight, 1), 8, r, "0") == "queued"
     # 48 cells along x per rank are not whole warp strips (64 FP64 cells): never dense
     small = Partition((96, 48, 48), r, 1, 2)
     assert fused_x_mode(small, owners(small, 1), 8, r, "1") == "queued"
@@ -160,18 +160,18 @@ def test_ctypes_structs_match_the_header(tmp_path):
     import os
     import subprocess
 
-    from stencil_b200._lib import AstarothParams, BoxCopy, HaloPush, Pitched
+    from stencil_b200._lib import AstarothParams, BoxCopy, HaloPush, Pitched, StepSync
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = tmp_path / "probe.c"
     src.write_text(
         '#include <stdio.h>\n#include "stencil_b200.h"\n'
-        'int main(void) { printf("%zu %zu %zu %zu\\n", sizeof(sb_pitched), sizeof(sb_box_copy), sizeof(sb_halo_push), sizeof(sb_astaroth_params)); return 0; }\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(sb_pitched), sizeof(sb_box_copy), sizeof(sb_halo_push), sizeof(sb_astaroth_params), sizeof(sb_step_sync)); return 0; }\n'
     )
     exe = tmp_path / "probe"
     subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
-    assert sizes == [C.sizeof(Pitched), C.sizeof(BoxCopy), C.sizeof(HaloPush), C.sizeof(AstarothParams)]
+    assert sizes == [C.sizeof(Pitched), C.sizeof(BoxCopy), C.sizeof(HaloPush), C.sizeof(AstarothParams), C.sizeof(StepSync)]
 
 
 def test_allocation_lead_rule(monkeypatch):
