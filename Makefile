@@ -22,13 +22,23 @@ APIFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -rdc=true --expt-extended-lambda -
              -Xcompiler -Wno-comment -x cu $(APIDEFS) $(APIINC)
 APISRC    := src/compat_kernels.cu src/local_domain.cu src/packer.cu src/translator.cu src/stencil.cu src/jacobi3d.cu \
              src/numeric.cpp src/timer.cpp src/rcstream.cpp src/topology.cpp src/gpu_topology.cpp \
-             src/placement_intranoderandom.cpp src/mpi_shim.cpp
+             src/placement_intranoderandom.cpp
 APIOBJ    := $(patsubst src/%,build/api/%.o,$(APISRC))
 # the core objects are compiled a second time with -rdc for the static library
 CAPIOBJ   := $(patsubst stencil_b200/csrc/%.cu,build/api/csrc_%.o,$(CSRC))
 LIBA      := lib/libstencil.a
+# the node-local MPI stand-in is a SEPARATE archive: link it only where no real MPI is (a second definition of MPI_*
+# inside libstencil.a would shadow or clash with the real one)
+LIBMPI    := lib/libmpi_shim.a
 
-all: $(SO) $(LIBA)
+all: $(SO) $(LIBA) $(LIBMPI) bin/sb_mpirun
+
+build/mpi_shim.o: src/mpi_shim.cpp include/mpi_shim/mpi.h
+	@mkdir -p build
+	g++ -O2 -std=c++17 -fPIC -Wall -Iinclude/mpi_shim -I/usr/local/cuda/include -c $< -o $@
+$(LIBMPI): build/mpi_shim.o
+	@mkdir -p lib
+	rm -f $@ && ar rcs $@ $^
 
 build/csrc/%.o: stencil_b200/csrc/%.cu $(wildcard stencil_b200/csrc/*.cuh) include/stencil_b200.h $(wildcard include/stencil/*.hpp)
 	@mkdir -p $(dir $@)
@@ -56,7 +66,7 @@ $(LIBA): $(APIOBJ) $(CAPIOBJ)
 # ---- the reference's unchanged drivers / tests against our library
 DRVFLAGS  := -O3 -std=c++14 $(ARCH) -lineinfo -rdc=true --expt-extended-lambda -Xcompiler -w -w -x cu $(APIDEFS) \
              -DCATCH_CONFIG_NO_POSIX_SIGNALS $(APIINC) -I$(REF)/thirdparty -I$(REF)/bin
-DRVLINK   := $(ARCH) -rdc=true -L/usr/local/cuda/lib64/stubs -lnvidia-ml -ldl -lcudart
+DRVLINK    = $(ARCH) -rdc=true -L/usr/local/cuda/lib64/stubs -lnvidia-ml -ldl -lcudart -lrt
 DRIVERS   := jacobi3d jacobi3d_strong bench_exchange bench_pack exchange_weak exchange_strong
 TESTCUDA  := test_cuda_main test_cuda_align test_cuda_local_domain test_cuda_pack test_cuda_packer test_cuda_rcstream \
              test_cuda_translate test_cuda_translate_kernel test_cuda_gpu_topo test_exchange
@@ -76,15 +86,15 @@ build/drv/t_%.o: $(REF)/test/%.cpp $(wildcard include/stencil/*)
 	@mkdir -p $(dir $@)
 	$(NVCC) $(DRVFLAGS) -c $< -o $@
 
-bin/%: build/drv/%.o build/drv/statistics.o $(LIBA)
+bin/%: build/drv/%.o build/drv/statistics.o $(LIBA) $(LIBMPI)
 	@mkdir -p bin
-	$(NVCC) $(DRVLINK) -o $@ $< build/drv/statistics.o $(LIBA)
+	$(NVCC) $(DRVLINK) -o $@ $< build/drv/statistics.o $(LIBA) $(LIBMPI)
 bin/test_cuda: $(patsubst %,build/drv/t_%.o,$(TESTCUDA)) $(LIBA)
 	@mkdir -p bin
-	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/t_%.o,$(TESTCUDA)) $(LIBA)
+	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/t_%.o,$(TESTCUDA)) $(LIBA) $(LIBMPI)
 bin/test_cpu: $(patsubst %,build/drv/t_%.o,$(TESTCPU)) $(LIBA)
 	@mkdir -p bin
-	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/t_%.o,$(TESTCPU)) $(LIBA)
+	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/t_%.o,$(TESTCPU)) $(LIBA) $(LIBMPI)
 
 # our own driver: the reference's jacobi3d loop over stencil::FusedJacobi3d (no reference sources involved)
 build/drv/jacobi3d_b200.o: drivers/jacobi3d_b200.cu $(wildcard include/stencil/*)
@@ -92,7 +102,12 @@ build/drv/jacobi3d_b200.o: drivers/jacobi3d_b200.cu $(wildcard include/stencil/*
 	$(NVCC) $(filter-out -I$(REF)/thirdparty -I$(REF)/bin,$(DRVFLAGS)) -c $< -o $@
 bin/jacobi3d_b200: build/drv/jacobi3d_b200.o $(LIBA)
 	@mkdir -p bin
-	$(NVCC) $(DRVLINK) -o $@ $< $(LIBA)
+	$(NVCC) $(DRVLINK) -o $@ $< $(LIBA) $(LIBMPI)
+
+# launcher of the node-local MPI shim (one rank per GPU without an MPI installation)
+bin/sb_mpirun: drivers/sb_mpirun.cpp $(LIBMPI)
+	@mkdir -p bin
+	g++ -O2 -std=c++17 -o $@ $< $(LIBMPI) -L/usr/local/cuda/lib64 -lcudart -lrt -lpthread
 
 # the baseline exchange driver (oracle/ref/ref_exchange_uniform.cu) against OUR library
 build/drv/exchange_uniform.o: oracle/ref/ref_exchange_uniform.cu $(wildcard include/stencil/*)
@@ -115,7 +130,7 @@ build/drv/astro_statistics.o: $(REF)/astaroth/statistics.cpp
 	$(NVCC) $(ASTROFLAGS) -c $< -o $@
 bin/astaroth: $(patsubst %,build/drv/astro_%.o,$(ASTRO)) build/drv/astro_statistics.o $(LIBA)
 	@mkdir -p bin
-	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/astro_%.o,$(ASTRO)) build/drv/astro_statistics.o $(LIBA)
+	$(NVCC) $(DRVLINK) -o $@ $(patsubst %,build/drv/astro_%.o,$(ASTRO)) build/drv/astro_statistics.o $(LIBA) $(LIBMPI)
 
 # the same driver with the reference's kernels.cu REPLACED by ours (src/astaroth_kernels.cu -> sb_astaroth_substep)
 build/drv/astro_b200_kernels.o: src/astaroth_kernels.cu include/stencil_b200.h $(wildcard include/stencil/*)
@@ -123,9 +138,9 @@ build/drv/astro_b200_kernels.o: src/astaroth_kernels.cu include/stencil_b200.h $
 	$(NVCC) $(ASTROFLAGS) -Iinclude -c $< -o $@
 bin/astaroth_b200: build/drv/astro_astaroth.o build/drv/astro_astaroth_utils.o build/drv/astro_b200_kernels.o build/drv/astro_statistics.o $(LIBA)
 	@mkdir -p bin
-	$(NVCC) $(DRVLINK) -o $@ build/drv/astro_astaroth.o build/drv/astro_astaroth_utils.o build/drv/astro_b200_kernels.o build/drv/astro_statistics.o $(LIBA)
+	$(NVCC) $(DRVLINK) -o $@ build/drv/astro_astaroth.o build/drv/astro_astaroth_utils.o build/drv/astro_b200_kernels.o build/drv/astro_statistics.o $(LIBA) $(LIBMPI)
 
-drivers: bin/jacobi3d_b200 $(patsubst %,bin/%,$(DRIVERS)) bin/test_cuda bin/test_cpu bin/exchange_uniform bin/astaroth bin/astaroth_b200 bin/test_exchange_multigpu
+drivers: bin/sb_mpirun bin/jacobi3d_b200 $(patsubst %,bin/%,$(DRIVERS)) bin/test_cuda bin/test_cpu bin/exchange_uniform bin/astaroth bin/astaroth_b200 bin/test_exchange_multigpu
 
 oracle:
 	$(MAKE) -C oracle

@@ -79,6 +79,28 @@ private:
   std::vector<RcStream> streams_; // one high-priority stream per local domain
   int parity_;
 
+  // Other ranks of this node (one process per GPU, started by sb_mpirun / mpirun).  Their allocations, staging buffers
+  // and flag mailboxes are mapped once, at realize(), through CUDA IPC handles that travel over MPI (the reference ships
+  // them the same way: include/stencil/tx_cuda.cuh:225-315, src/tx_ipc.cpp).  After that the data path is the fused
+  // copy kernel storing into the mapped ghost cells; the only cross-rank synchronisation of an exchange is a pair of
+  // device-side flags per neighbour rank (ready: "my ghost cells may be overwritten for exchange e"; done: "my writes
+  // into you for exchange e have landed"), st.release.sys / ld.acquire.sys by tiny kernels -- no MPI call, no host sync.
+  struct RemoteDomain {
+    Dim3 raw;
+    std::vector<char *> curr, next; // mapped allocations per quantity, in the owner's parity-0 naming
+  };
+  std::map<Dim3, RemoteDomain> remote_;                       // neighbour subdomains of other ranks
+  std::map<std::pair<Dim3, Dim3>, char *> remoteStage_;       // (src idx, dst idx) -> staging buffer in the dst rank
+  std::vector<void *> ipcOpened_;
+  uint32_t *mailbox_;                // my mailbox: ready[worldSize] then done[worldSize]
+  std::vector<uint32_t *> peerFlags_; // per rank: its mailbox (mapped), nullptr for non-neighbours
+  std::vector<int> nbrRanks_;
+  uint32_t epoch_;
+  void share_with_ranks(const std::map<std::pair<Dim3, Dim3>, char *> &myStage);
+  void close_ranks();
+  void flags_begin();
+  void flags_finish();
+
   std::string outputPrefix_;
 
   // payload bytes per exchange, attributed the way the reference's planner attributes them
@@ -147,6 +169,9 @@ public:
   std::vector<Rect3> get_interior() const;
   std::vector<std::vector<Rect3>> get_exterior() const;
 
+  int rank() const noexcept { return rank_; }
+  const Radius &radius() const noexcept { return radius_; }
+  const Dim3 &domain_index(size_t i) const { return domainIdx_[i]; }
   const Topology &get_topology() const noexcept { return topology_; }
   Placement *get_placement() const noexcept { return placement_; }
 

@@ -143,7 +143,8 @@ int sb_jacobi3d_regions(sb_pitched dst, sb_pitched src, int dtype_size, const in
  * (what the driver passes as Rect3 cr, astaroth/astaroth.cu:563-566); every cell needs 3 allocated cells around it.
  * step 0..2 = Williamson RK3 substep; step 0 ignores the previous contents of `out`.
  * params: the uniforms solve<> reads through DCONST (acDeviceLoadMeshInfo / acDeviceLoadScalarUniform,
- * astaroth/kernels.cu:89-163).  variant: 0 auto, 1 cell kernel, 2 tile kernel.
+ * astaroth/kernels.cu:89-163).  variant: 0 auto, 1 cell kernel, 2 tile kernel (one thread per cell), 3 team kernel (two specialised
+ * threads per cell on the same shared-memory ring).
  * dtype_size 8 = double (the reference's AcReal), 4 = float.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -181,24 +182,23 @@ int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int6
                       const int64_t hi[3], const int64_t clo[3], const int64_t chi[3], const sb_halo_push *push, void *stream);
 /* The same launch with the ordering BETWEEN RANKS inside the kernel, replacing the reference's per-iteration host
  * synchronisation (DistributedDomain::exchange() returns after MPI_Waitall / stream syncs, src/stencil.cu:1120-1186;
- * bin/jacobi3d.cu:337-365) and this library's own sb_wait / sb_signal launches.  Only the CTAs on a face of the
- * subdomain read ghost cells or write into a neighbour, so only they take part: before marching they poll
- * wait_slots[i] (mailbox words in THIS GPU's memory, one per neighbour rank; ld.acquire.sys) until
- * (int32)(*slot - wait_value) >= 0; after marching each fences its pushes and counts itself into *arrive, and the last
- * one stores signal_value into signal_slots[i] (the neighbours' mailbox words for this rank, peer / IPC mapped;
- * st.release.sys) and resets *arrive.  Protocol: iteration e waits for e and signals e + 1 -- a neighbour that has
- * finished iteration e - 1 has (a) pushed the ghost values iteration e reads and (b) stopped reading the ghost cells
- * iteration e overwrites.  order: 0 natural block order, 1 boundary CTAs dispatched first (the inner ~64 % of the CTAs
- * then absorb the skew between ranks), 2 boundary CTAs last, -1 library default.  epoch (optional, device word): added
- * to both values and incremented by the kernel, so a captured CUDA graph can be replayed.  sync == NULL: no handshake. */
+ * bin/jacobi3d.cu:337-365) and this library's own sb_wait / sb_signal launches.
+ * The kernel ships every face in GROUPS of ~2048 cells (x faces: 64 rows x one z chunk of 32 planes of the column; y faces:
+ * one 32-lane strip of the row x one z chunk; z faces: 8 rows of the plane -- the index arithmetic is the kernel's, the same
+ * on both sides of a face); the last CTA of a group stores the slab into the neighbour, fences at system scope and
+ * writes signal_value into signal_rows[f][group] -- a uint32 array of SB_FUSED_MAX_GROUPS words in the NEIGHBOUR's memory
+ * (peer / IPC mapped): its mailbox row for the face it shares with this subdomain.  Before marching, a CTA on face f polls
+ * wait_rows[f][group] (this GPU's own mailbox row for face f, written by the neighbour across f; ld.acquire.sys) until
+ * (int32)(word - wait_value) >= 0.  Protocol: iteration e waits for e and signals e + 1 -- a neighbour that has shipped
+ * group g of iteration e - 1 has (a) filled the ghost cells iteration e reads there and (b) stopped reading the ghost cells
+ * iteration e overwrites there.  Neighbours walk their grids in the same order, so in steady state every word was written
+ * an iteration earlier and nobody spins.  Faces: -x,+x,-y,+y,-z,+z.  NULL rows: no wait / no signal on that face
+ * (neighbour in the same process: order the launches with stream events).  sync == NULL: no handshake at all. */
+#define SB_FUSED_MAX_GROUPS 1024
 typedef struct {
-  const uint32_t *wait_slots[6];
-  uint32_t *signal_slots[6];
-  uint32_t *arrive; /* device word, zero before the first launch */
-  uint32_t *epoch;  /* device word or NULL */
-  int32_t n_wait, n_signal;
+  const uint32_t *wait_rows[6];
+  uint32_t *signal_rows[6];
   uint32_t wait_value, signal_value;
-  int32_t order;
 } sb_step_sync;
 int sb_jacobi3d_fused_sync(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3],
                            const int64_t hi[3], const int64_t clo[3], const int64_t chi[3], const sb_halo_push *push,

@@ -66,6 +66,9 @@ for stage in "$@"; do
   ncu_fused)
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:jacobi_fused_kernel -s 4 -c 1 -o "$F/prof_jacobi_fused" -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity >"$F/ncu_full.log" 2>&1
     tail -3 "$F/ncu_full.log" ;;
+  ncu_astaroth) # the astaroth substep kernels, FP64 256^3 (variant in SB_AC_VARIANTS, default "team tile")
+    SKIP_CELL=1 SKIP_ITER=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ac_t -c 6 -o "$F/prof_astaroth_f64" -f python scripts/time_astaroth.py 256 f64 1 >"$F/ncu_astaroth.log" 2>&1
+    tail -3 "$F/ncu_astaroth.log" ;;
   sanitize) # memcheck on the small fused cases
     timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_jacobi.py -q -m gpu -x -k "block_orders and float64" 2>&1 | tail -15 | tee "$F/sanitize.txt" ;;
   cpp) # the C++ API: the reference's own suites and drivers against our library

@@ -47,11 +47,11 @@ def timeit(fn, reps=reps):
 
 
 tag = os.environ.get("SB_AC_SHAPE", "0") + "/" + os.environ.get("SB_AC_ZCHUNK", "auto")
-for variant, name in ((ac.TILE, "tile"), (ac.CELL, "cell")):
+for variant, name in ((ac.TEAM, "team"), (ac.TILE, "tile"), (ac.CELL, "cell")):
     if variant == ac.CELL and os.environ.get("SKIP_CELL"):
         continue
     for step in range(3):
-        ms = timeit(lambda: ac.substep(step, cur, nxt, es, (m, m, m), (3, 3, 3), (m - 3, m - 3, m - 3), params, variant, stream), reps if variant == ac.TILE else 2)
+        ms = timeit(lambda: ac.substep(step, cur, nxt, es, (m, m, m), (3, 3, 3), (m - 3, m - 3, m - 3), params, variant, stream), reps if variant != ac.CELL else 2)
         alg = (16 if step == 0 else 24) * es * cells
         print(f"[{np.dtype(dtype).name} n={n} shape/zc={tag}] {name} substep {step}: {ms:.4f} ms  {cells/ms/1e6:.1f} Gcell/s  {alg/ms/1e6:.0f} GB/s algorithmic = {alg/ms/1e6/peak*100:.1f}% of HBM peak", flush=True)
 if not os.environ.get("SKIP_ITER"):

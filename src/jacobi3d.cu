@@ -37,6 +37,13 @@ FusedJacobi3d::FusedJacobi3d(DistributedDomain &dd, size_t quantity, size_t elem
 
   Placement *pl = dd_.get_placement();
   const Topology &topo = dd_.get_topology();
+  // neighbours owned by another rank: the exchange() of the reference schedule reaches them (CUDA-IPC direct writes +
+  // device-side flags); the fused kernel's in-kernel handshake across ranks is wired up in the Python layer only
+  for (size_t di = 0; fused_ && di < doms.size(); ++di)
+    for (const Dim3 &f : kFaces) {
+      const Topology::OptionalNeighbor nb = topo.get_neighbor(dd_.domain_index(di), f);
+      if (nb.exists && pl->get_rank(nb.index) != dd_.rank()) fused_ = false;
+    }
   const Rect3 whole = dd_.get_compute_region();
   const std::vector<Rect3> interiors = dd_.get_interior();
   const std::vector<std::vector<Rect3>> exteriors = dd_.get_exterior();
@@ -72,9 +79,6 @@ FusedJacobi3d::FusedJacobi3d(DistributedDomain &dd, size_t quantity, size_t elem
         for (int k = 0; k < 6; ++k) {
           const Topology::OptionalNeighbor nb = topo.get_neighbor(idx, kFaces[k]);
           if (!nb.exists) continue; // non-periodic boundary: nothing to push
-          if (pl->get_rank(nb.index) != mpi::world_rank()) {
-            LOG_FATAL("FusedJacobi3d: neighbour subdomain " << nb.index << " lives on another rank (C++ API: one rank x N GPUs)");
-          }
           const size_t dj = size_t(pl->get_subdomain_id(nb.index));
           const LocalDomain &n = doms[dj];
           // the neighbour's OUTPUT buffer of this iteration

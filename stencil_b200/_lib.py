@@ -50,20 +50,13 @@ class HaloPush(C.Structure):
     _fields_ = [("nbr", Pitched * 6), ("nbr_zsize", C.c_int64 * 6), ("x_dense", C.c_int64 * 2), ("x_recv", C.c_void_p * 2)]
 
 
-class StepSync(C.Structure):
-    """sb_step_sync: the in-kernel handshake of sb_jacobi3d_fused_sync (mailbox slots of the neighbour ranks)."""
+FUSED_MAX_GROUPS = 1024  # SB_FUSED_MAX_GROUPS
 
-    _fields_ = [
-        ("wait_slots", C.c_void_p * 6),
-        ("signal_slots", C.c_void_p * 6),
-        ("arrive", C.c_void_p),
-        ("epoch", C.c_void_p),
-        ("n_wait", C.c_int32),
-        ("n_signal", C.c_int32),
-        ("wait_value", C.c_uint32),
-        ("signal_value", C.c_uint32),
-        ("order", C.c_int32),
-    ]
+
+class StepSync(C.Structure):
+    """sb_step_sync: per-face mailbox rows of the in-kernel handshake of sb_jacobi3d_fused_sync."""
+
+    _fields_ = [("wait_rows", C.c_void_p * 6), ("signal_rows", C.c_void_p * 6), ("wait_value", C.c_uint32), ("signal_value", C.c_uint32)]
 
 
 # every symbol include/stencil_b200.h declares: (restype, argtypes)

@@ -19,6 +19,7 @@
 // DFMA-issue bound before it is HBM bound -- numbers in profiles/README.md.
 #include "astaroth.cuh"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -29,6 +30,7 @@ enum { LNRHO = 0, UUX, UUY, UUZ, AX, AY, AZ, ENTROPY };
 
 template <typename T> struct AcConst {
   T ix, iy, iz, dt, cs2s, gam, cp, lnrho0, lnT0, mu0, nu, zeta, eta;
+  T icp, imu0, elnT0; // 1 / cp, 1 / mu0, exp(lnT0): hoisted to the host (team kernel)
 };
 
 template <typename T> AcConst<T> make_const(const AcParams &p) {
@@ -36,6 +38,7 @@ template <typename T> AcConst<T> make_const(const AcParams &p) {
   c.ix = T(p.inv_dsx), c.iy = T(p.inv_dsy), c.iz = T(p.inv_dsz), c.dt = T(p.dt);
   c.cs2s = T(p.cs2_sound), c.gam = T(p.gamma), c.cp = T(p.cp_sound), c.lnrho0 = T(p.lnrho0), c.lnT0 = T(p.lnT0);
   c.mu0 = T(p.mu0), c.nu = T(p.nu_visc), c.zeta = T(p.zeta), c.eta = T(p.eta);
+  c.icp = T(1.0 / p.cp_sound), c.imu0 = T(1.0 / p.mu0), c.elnT0 = T(exp(p.lnT0));
   return c;
 }
 
@@ -328,6 +331,254 @@ __global__ void __launch_bounds__(TX *TY, 1) ac_tile_kernel(const __grid_constan
   }
 }
 
+int env_int(const char *name, int dflt);
+
+// ---------------------------------------------------------------------------------------------- team kernel
+// Two threads per cell.  The tile kernel above keeps value + gradient + hessian of all 8 fields live until the physics
+// runs (238 registers -> 7 warps per SM), and all of its warps alternate between a shared-memory phase (296 LDS) and an
+// FP64 phase (~900 instructions) in lock step behind the per-plane barrier: ncu shows the two pipes at 53 % and 31 %,
+// never overlapping (profiles/astaroth_tile_f64_r1_v1.summary.txt).  Here
+//   team U (threads [0, NC))      derives lnrho, entropy, uux, uuy, uuz and folds every field into a handful of running
+//                                 sums the moment it is derived (advection, div u, lap u, grad div u, the six entries of
+//                                 the rate-of-strain tensor, ...), then integrates continuity, momentum and entropy;
+//   team A (threads [NC, 2 NC))   derives ax, ay, az (curl, laplacian, grad div), integrates the induction equation and
+//                                 hands j x B and |j|^2 to team U through 4 words of shared memory per cell.
+// Nobody holds more than ~35 live values, the CTA has twice the warps on the same shared-memory ring, and the two teams
+// have different LDS : FP64 mixes, so one team's loads overlap the other's arithmetic.  The only intra-plane dependency
+// is a named barrier (team A arrives, team U waits) just before team U's final assembly.
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int STEP, typename T, int TX, int TY, int NSLOT>
+__global__ void __launch_bounds__(2 * TX *TY, 1) ac_team_kernel(const __grid_constant__ AcArgs<T> A) {
+  constexpr int W = TX + 6, H = TY + 6, PL = W * H, NC = TX * TY, NT = 2 * NC, NL = (PL + NT - 1) / NT;
+  static_assert(NSLOT == 8, "ring of 8 planes: 7 in use + 1 in flight");
+  extern __shared__ __align__(16) unsigned char ac_smem[];
+  T *ring = reinterpret_cast<T *>(ac_smem);      // [field][slot][H][W]
+  T *xb = ring + kAcFields * NSLOT * PL;         // [4][NC]: (j x B).xyz, |j|^2 of the plane in progress
+
+  const int tid = threadIdx.x;
+  const bool teamA = tid >= NC;
+  const int cell = teamA ? tid - NC : tid;
+  const int tx = cell % TX, ty = cell / TX;
+  const int x0 = A.lo[0] + blockIdx.x * TX, y0 = A.lo[1] + blockIdx.y * TY;
+  const int z0 = A.lo[2] + blockIdx.z * A.zchunk;
+  const int z1 = min(z0 + A.zchunk, A.hi[2]);
+  const int mx = A.mx;
+  const long long mxy = A.mxy;
+  const AcConst<T> &P = A.P;
+
+  int goff[NL];
+#pragma unroll
+  for (int k = 0; k < NL; ++k) {
+    const int e = tid + k * NT;
+    const int r = e / W, c = e - r * W;
+    const int gx = min(x0 - 3 + c, mx - 1), gy = min(y0 - 3 + r, A.my - 1); // partial tiles: stay inside the allocation
+    goff[k] = (e < PL) ? gy * mx + gx : -1;
+  }
+  auto load_plane = [&](int p, int slot) {
+#pragma unroll
+    for (int f = 0; f < kAcFields; ++f) {
+      const T *src = A.in[f] + (long long)p * mxy;
+      T *dst = ring + (f * NSLOT + slot) * PL + tid;
+#pragma unroll
+      for (int k = 0; k < NL; ++k) {
+        if (goff[k] >= 0) cp_async<sizeof(T)>(dst + k * NT, src + goff[k]);
+      }
+    }
+  };
+  for (int p = z0 - 3; p <= z0 + 3; ++p) load_plane(p, p - z0 + 3);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+
+  const bool valid = (x0 + tx < A.hi[0]) && (y0 + ty < A.hi[1]);
+  const int o0 = (ty + 3) * W + tx + 3;
+  long long idx = (long long)z0 * mxy + (long long)(y0 + ty) * mx + (x0 + tx);
+  const T third = T(1.0) / T(3.0), half = T(0.5);
+
+  for (int z = z0; z < z1; ++z, idx += mxy) {
+    const int zi = z - z0;
+    if (z + 1 < z1) load_plane(z + 4, (zi + 7) % NSLOT);
+    cp_async_commit();
+    const T *b[7]; // plane z-3+k of field 0 at this thread's cell
+#pragma unroll
+    for (int k = 0; k < 7; ++k) b[k] = ring + ((zi + k) % NSLOT) * PL + o0;
+    auto atf = [&](int f) {
+      return [&b, f](int dx, int dy, int dz) { return b[dz + 3][f * NSLOT * PL + dy * W + dx]; };
+    };
+    const T ux = b[3][UUX * NSLOT * PL], uy = b[3][UUY * NSLOT * PL], uz = b[3][UUZ * NSLOT * PL];
+    if (teamA) {
+      if (valid) {
+        T pa[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pa[i] = (STEP == 0) ? T(0) : A.out[AX + i][idx];
+        // curl A, laplacian A, grad div A, folded field by field
+        T Bx, By, Bz, lax, lay, laz, gx, gy, gz, av[3];
+        {
+          const Dv<T> d = derive<T, true, true, false>(atf(AX), P);
+          av[0] = d.v;
+          By = d.gz, Bz = -d.gy;
+          lax = d.xx + d.yy + d.zz;
+          gx = d.xx, gy = d.xy, gz = d.xz;
+        }
+        {
+          const Dv<T> d = derive<T, true, false, true>(atf(AY), P);
+          av[1] = d.v;
+          Bx = -d.gz, Bz += d.gx;
+          lay = d.xx + d.yy + d.zz;
+          gx += d.xy, gy += d.yy, gz += d.yz;
+        }
+        {
+          const Dv<T> d = derive<T, false, true, true>(atf(AZ), P);
+          av[2] = d.v;
+          Bx += d.gy, By -= d.gx;
+          laz = d.xx + d.yy + d.zz;
+          gx += d.xz, gy += d.yz, gz += d.zz;
+        }
+        const T indx = (uy * Bz - uz * By) + P.eta * lax;
+        const T indy = (uz * Bx - ux * Bz) + P.eta * lay;
+        const T indz = (ux * By - uy * Bx) + P.eta * laz;
+        const T jx = P.imu0 * (gx - lax), jy = P.imu0 * (gy - lay), jz = P.imu0 * (gz - laz);
+        xb[0 * NC + cell] = jy * Bz - jz * By;
+        xb[1 * NC + cell] = jz * Bx - jx * Bz;
+        xb[2 * NC + cell] = jx * By - jy * Bx;
+        xb[3 * NC + cell] = jx * jx + jy * jy + jz * jz;
+        A.out[AX][idx] = rk3<STEP>(pa[0], av[0], indx, P.dt);
+        A.out[AY][idx] = rk3<STEP>(pa[1], av[1], indy, P.dt);
+        A.out[AZ][idx] = rk3<STEP>(pa[2], av[2], indz, P.dt);
+      }
+      __threadfence_block();
+      bar_arrive(1, NT);
+    } else {
+      T pl = T(0), ps = T(0), pu[3] = {T(0), T(0), T(0)};
+      T lrv = T(0), sv = T(0), cont = T(0), entadv = T(0), heat_in = T(0), arg = T(0);
+      T lg[3] = {T(0), T(0), T(0)}, G[3] = {T(0), T(0), T(0)};
+      T madv[3], lu[3], gd[3], divu = T(0), S00 = T(0), S11 = T(0), S22 = T(0), S01 = T(0), S02 = T(0), S12 = T(0);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) madv[i] = lu[i] = gd[i] = T(0);
+      if (valid) {
+        if (STEP != 0) {
+          pl = A.out[LNRHO][idx], ps = A.out[ENTROPY][idx];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) pu[i] = A.out[UUX + i][idx];
+        }
+        T llr;
+        {
+          const Dv<T> d = derive<T, false, false, false>(atf(LNRHO), P);
+          lrv = d.v;
+          lg[0] = d.gx, lg[1] = d.gy, lg[2] = d.gz;
+          llr = d.xx + d.yy + d.zz;
+          cont = -(ux * d.gx + uy * d.gy + uz * d.gz);
+        }
+        {
+          const Dv<T> d = derive<T, false, false, false>(atf(ENTROPY), P);
+          sv = d.v;
+          const T ls = d.xx + d.yy + d.zz;
+          const T sg[3] = {d.gx, d.gy, d.gz};
+          const T first = P.gam * P.icp * ls + (P.gam - T(1.0)) * llr;
+          T dot = T(0);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            G[i] = P.icp * sg[i] + lg[i];
+            const T s2 = P.gam * P.icp * sg[i] + (P.gam - T(1.0)) * lg[i];
+            const T t3 = P.gam * G[i] + (-lg[i]);
+            dot += s2 * t3;
+          }
+          heat_in = first + dot;
+          entadv = -(ux * d.gx + uy * d.gy + uz * d.gz);
+          arg = P.gam * d.v * P.icp + (P.gam - T(1.0)) * (lrv - P.lnrho0);
+        }
+        {
+          const Dv<T> d = derive<T, true, true, false>(atf(UUX), P);
+          madv[0] = -(d.gx * ux + d.gy * uy + d.gz * uz);
+          divu = d.gx;
+          lu[0] = d.xx + d.yy + d.zz;
+          gd[0] = d.xx, gd[1] = d.xy, gd[2] = d.xz;
+          S00 = (T(2.0) * third) * d.gx, S11 = -third * d.gx, S22 = S11;
+          S01 = half * d.gy, S02 = half * d.gz;
+        }
+        {
+          const Dv<T> d = derive<T, true, false, true>(atf(UUY), P);
+          madv[1] = -(d.gx * ux + d.gy * uy + d.gz * uz);
+          divu += d.gy;
+          lu[1] = d.xx + d.yy + d.zz;
+          gd[0] += d.xy, gd[1] += d.yy, gd[2] += d.yz;
+          S00 -= third * d.gy, S11 += (T(2.0) * third) * d.gy, S22 -= third * d.gy;
+          S01 += half * d.gx, S12 = half * d.gz;
+        }
+        {
+          const Dv<T> d = derive<T, false, true, true>(atf(UUZ), P);
+          madv[2] = -(d.gx * ux + d.gy * uy + d.gz * uz);
+          divu += d.gz;
+          lu[2] = d.xx + d.yy + d.zz;
+          gd[0] += d.xz, gd[1] += d.yz, gd[2] += d.zz;
+          S00 -= third * d.gz, S11 -= third * d.gz, S22 += (T(2.0) * third) * d.gz;
+          S02 += half * d.gx, S12 += half * d.gy;
+        }
+      }
+      bar_sync(1, NT); // team A's j x B and |j|^2 of this plane are in xb
+      if (valid) {
+        const T jxB[3] = {xb[0 * NC + cell], xb[1 * NC + cell], xb[2 * NC + cell]};
+        const T j2 = xb[3 * NC + cell];
+        const T earg = ac_exp(arg);
+        const T cs2 = P.cs2s * earg;
+        const T rho = ac_exp(lrv);
+        const T inv_rho = T(1.0) / rho;
+        const T Sg[3] = {S00 * lg[0] + S01 * lg[1] + S02 * lg[2], S01 * lg[0] + S11 * lg[1] + S12 * lg[2], S02 * lg[0] + S12 * lg[1] + S22 * lg[2]};
+        const T uv[3] = {ux, uy, uz};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          T m = madv[i] - cs2 * G[i];
+          m = m + inv_rho * jxB[i];
+          m = m + P.nu * ((lu[i] + third * gd[i]) + T(2.0) * Sg[i]);
+          m = m + P.zeta * gd[i];
+          A.out[UUX + i][idx] = rk3<STEP>(pu[i], uv[i], m, P.dt);
+        }
+        A.out[LNRHO][idx] = rk3<STEP>(pl, lrv, cont - divu, P.dt);
+        // exp(lnT) = exp(lnT0) * exp(arg): the reference evaluates a third exp (rounding-level difference)
+        const T inv_pT = T(1.0) / (rho * (P.elnT0 * earg));
+        const T SS = (S00 * S00 + S01 * S01 + S02 * S02) + (S01 * S01 + S11 * S11 + S12 * S12) + (S02 * S02 + S12 * S12 + S22 * S22);
+        const T RHS = P.eta * P.mu0 * j2 + T(2.0) * rho * P.nu * SS + P.zeta * rho * divu * divu;
+        const T chi = T(0.001) / (rho * P.cp);
+        const T ent = entadv + inv_pT * RHS + P.cp * chi * heat_in;
+        A.out[ENTROPY][idx] = rk3<STEP>(ps, sv, ent, P.dt);
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+  }
+}
+
+template <int STEP, typename T, int TX, int TY> int launch_team(AcArgs<T> &A, cudaStream_t stream) {
+  constexpr int NSLOT = 8;
+  constexpr size_t smem = (size_t(kAcFields) * NSLOT * (TX + 6) * (TY + 6) + 4 * TX * TY) * sizeof(T);
+  static unsigned long long configured = 0;
+  auto kern = ac_team_kernel<STEP, T, TX, TY, NSLOT>;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (!(configured >> (dev & 63) & 1)) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return -1;
+    configured |= 1ull << (dev & 63);
+  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ex = A.hi[0] - A.lo[0], ey = A.hi[1] - A.lo[1], ez = A.hi[2] - A.lo[2];
+  const int gx = (ex + TX - 1) / TX, gy = (ey + TY - 1) / TY;
+  int best_len = ez;
+  long long best_cost = -1;
+  for (int n = 1; n <= ez && n <= 64; ++n) { // see launch_tile
+    const int len = (ez + n - 1) / n;
+    const long long ctas = (long long)gx * gy * ((ez + len - 1) / len);
+    const long long cost = ((ctas + sms - 1) / sms) * (len + 4);
+    if (best_cost < 0 || cost < best_cost) best_cost = cost, best_len = len;
+  }
+  const int forced = env_int("SB_AC_ZCHUNK", 0);
+  A.zchunk = forced > 0 ? (forced < ez ? forced : ez) : best_len;
+  dim3 grid(gx, gy, (ez + A.zchunk - 1) / A.zchunk);
+  kern<<<grid, 2 * TX * TY, smem, stream>>>(A);
+  return 1;
+}
+
 int env_int(const char *name, int dflt) {
   const char *s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;
@@ -379,6 +630,10 @@ template <int STEP, typename T> int launch_step(AcArgs<T> &A, int variant, cudaS
   const int ex = A.hi[0] - A.lo[0], ey = A.hi[1] - A.lo[1], ez = A.hi[2] - A.lo[2];
   if (variant == AC_AUTO) variant = (ex >= 8 && ey >= 8 && ez >= 8) ? AC_TILE : AC_CELL;
   if (variant == AC_CELL) return launch_cell<STEP>(A, stream);
+  if (variant == AC_TEAM) {
+    if constexpr (sizeof(T) == 8) return launch_team<STEP, T, 16, 12>(A, stream);
+    else return launch_team<STEP, T, 32, 8>(A, stream);
+  }
   const int shape = env_int("SB_AC_SHAPE", 0);
   if constexpr (sizeof(T) == 8) {
     if (shape == 1) return launch_tile<STEP, T, 16, 16, 7>(A, stream);

@@ -27,7 +27,8 @@ struct AcFields {
 enum AcVariant {
   AC_AUTO = 0,   // tile kernel for thick regions, cell kernel for thin ones
   AC_CELL = 1,   // one thread per cell, neighbours through L1/L2
-  AC_TILE = 2,   // z-march over a shared-memory ring of halo'd planes (cp.async pipeline)
+  AC_TILE = 2,   // z-march over a shared-memory ring of halo'd planes (cp.async pipeline), one thread per cell
+  AC_TEAM = 3,   // the same ring, two specialised threads per cell (velocity/thermodynamics team + induction team)
 };
 
 // solve<step> on the box [lo, hi) in memory-offset coordinates (the reference's IDX(i,j,k) = i + j*mx + k*mx*my);

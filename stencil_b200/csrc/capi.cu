@@ -772,26 +772,13 @@ int sb_jacobi3d_fused_sync(sb_pitched dst, sb_pitched src, int dtype_size, const
                            const int64_t clo[3], const int64_t chi[3], const sb_halo_push *push, const sb_step_sync *sync, void *stream) {
   if (!push) return fail(SB_ERR_INVALID, "null push table");
   sb::FusedSync fs{};
-  fs.order = -1;
   if (sync) {
-    if (sync->n_wait < 0 || sync->n_wait > 6 || sync->n_signal < 0 || sync->n_signal > 6)
-      return fail(SB_ERR_INVALID, "between 0 and 6 neighbour slots per direction of the handshake");
-    if (sync->n_signal > 0 && !sync->arrive) return fail(SB_ERR_INVALID, "signalling needs the arrive counter");
-    for (int i = 0; i < sync->n_wait; ++i) {
-      if (!sync->wait_slots[i]) return fail(SB_ERR_INVALID, "null wait slot %d", i);
-      fs.wait_slot[i] = sync->wait_slots[i];
+    for (int f = 0; f < 6; ++f) {
+      fs.wait_row[f] = sync->wait_rows[f];
+      fs.signal_row[f] = sync->signal_rows[f];
     }
-    for (int i = 0; i < sync->n_signal; ++i) {
-      if (!sync->signal_slots[i]) return fail(SB_ERR_INVALID, "null signal slot %d", i);
-      fs.signal_slot[i] = sync->signal_slots[i];
-    }
-    fs.n_wait = sync->n_wait;
-    fs.n_signal = sync->n_signal;
     fs.wait_value = sync->wait_value;
     fs.signal_value = sync->signal_value;
-    fs.arrive = sync->arrive;
-    fs.epoch = sync->epoch;
-    fs.order = sync->order;
   }
   sb::JacobiParams p{};
   int rc = to_alloc_box(src, dtype_size, acc_origin, lo, hi, p.lo, p.hi);
@@ -823,8 +810,6 @@ int sb_jacobi3d_fused_sync(sb_pitched dst, sb_pitched src, int dtype_size, const
     const long long fixed = (d % 2 == 0) ? nraw[axis] - 1 : 0;
     if (nraw[axis] < 3) return fail(SB_ERR_INVALID, "neighbour %d allocation too small", d);
     const long long stride[3] = {(long long)dtype_size, npitch, nslice};
-    if (axis == 0 && nslice != src.pitch * src.ysize)
-      return fail(SB_ERR_INVALID, "x neighbour %d must have this subdomain's plane size (fused x push advances both by one slice)", d);
     p.push_ptr[d] = static_cast<char *>(n.ptr) + fixed * stride[axis];
     p.push_pitch[d] = npitch;
     p.push_slice[d] = nslice;
@@ -844,7 +829,9 @@ int sb_jacobi3d_fused_sync(sb_pitched dst, sb_pitched src, int dtype_size, const
   if (self(0) && self(1)) p.xwrap = 1; // a request: launch_jacobi_fused keeps the x pushes when the vector layout rules it out
   if (self(2) && self(3) && (src.pitch % 16 == 0 || (p.hi[1] - p.lo[1]) % 2 == 0)) p.ywrap = 1, p.push_ptr[2] = p.push_ptr[3] = nullptr;
   const int n = sb::launch_jacobi_fused(p, fs, dtype_size, static_cast<cudaStream_t>(stream));
-  if (n < 0) return fail(SB_ERR_INVALID, "dense x faces need a 16-byte aligned first compute cell, whole warp strips along x and z chunks of <= 32 planes");
+  if (n == -1) return fail(SB_ERR_INVALID, "a dense received x array needs a 16-byte aligned first compute cell and whole warp strips along x");
+  if (n == -2) return fail(SB_ERR_INVALID, "more than %d z chunks or tile rows: too tall for the fused kernel's face groups", SB_FUSED_MAX_GROUPS);
+  if (n < 0) return fail(SB_ERR_CUDA, "cannot allocate the face-group counters");
   g_launches += uint64_t(n);
   SB_CUDA(cudaGetLastError());
   return SB_OK;
@@ -855,7 +842,7 @@ int sb_astaroth_substep(int step, const void *const in[8], void *const out[8], i
   if (!in || !out || !raw || !lo || !hi || !params) return fail(SB_ERR_INVALID, "null argument");
   if (step < 0 || step > 2) return fail(SB_ERR_INVALID, "substep %d (Williamson RK3 has substeps 0, 1, 2)", step);
   if (dtype_size != 4 && dtype_size != 8) return fail(SB_ERR_INVALID, "dtype_size %d (4 = float, 8 = double)", dtype_size);
-  if (variant < 0 || variant > 2) return fail(SB_ERR_INVALID, "variant %d", variant);
+  if (variant < 0 || variant > 3) return fail(SB_ERR_INVALID, "variant %d", variant);
   sb::AcFields f;
   for (int i = 0; i < sb::kAcFields; ++i) {
     if (!in[i] || !out[i]) return fail(SB_ERR_INVALID, "field %d is null", i);

@@ -16,6 +16,10 @@
 // to the CPU oracle's `v / 6` in both FP32 and FP64.
 #include "jacobi.cuh"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace sb {
 namespace {
 
@@ -68,13 +72,12 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // loads, stores) stay full 128-bit vectors on every row; only the two L1-resident neighbour rows
 // (y-1, y+1), which have the opposite phase, are fetched as two half vectors.
 //
-// PUSH variant (RY = 1): the region is the whole compute region of the subdomain and every boundary cell is stored a
-// second time -- into the ghost cell of the face neighbour that will read it next iteration (own memory for a
-// periodic self-neighbour, a peer GPU's memory over NVLink otherwise): x faces inside the loop (one predicated branch
-// per step, taken by two lanes per row), y and z faces by an epilogue over the few warps that own them.
-// The halo exchange of the next iteration is thereby part of this kernel: no pack / unpack pass over the 8-byte-wide
-// x faces, no separate exterior kernel.
-template <typename T, int VX, int RY, bool SHIFT, int PUSH> // PUSH: 0 plain, 1 fused halo push, 2 fused without x pushes, 3 fused with dense x faces
+// EDGE variants (RY = 1; the boundary CTAs of the fused kernel): identical to the plain loop except for where the cells
+// just outside the subdomain come from -- a periodic self-neighbour is read in place from the opposite face of src
+// (pointer set-up before the loop), and the x neighbour of the first / last column may come from a dense received array
+// instead of the ghost column (EDGE = 3).  Nothing is pushed inside the loop: the faces are shipped afterwards by the
+// last CTA of each face group (jacobi_fused_kernel).
+template <typename T, int VX, int RY, bool SHIFT, int PUSH> // PUSH (= EDGE): 0 plain, 2 boundary CTA, 3 boundary CTA with dense x ghosts
 __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, const int by, const int bz) {
   static_assert(!SHIFT || (RY == 1 && VX >= 2), "the phase-shifted variant handles one row per warp");
   static_assert(!PUSH || RY == 1, "the push variant handles one row per warp");
@@ -154,49 +157,6 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   }
   const int gx0 = x + p.org[0];
 
-  // PUSH, x faces: the one lane of a row that holds the first (last) compute cell stores it a second time, into the
-  // ghost cell of the -x (+x) neighbour.  Both addresses advance by one slice per plane (the launcher checks that the
-  // neighbour's slice equals ours), so the loop carries nothing for it: `xdiff` is the constant distance between the two,
-  // and the marching loop pays one predicated branch per step.
-  long long xdiff = 0;
-  bool xpush = false;
-  if (PUSH == 1 && row_ok[0]) {
-#pragma unroll
-    for (int i = 0; i < VX; ++i) {
-      const int d = (x + i == p.lo[0]) ? 0 : ((x + i == p.hi[0] - 1) ? 1 : -1);
-      if (d >= 0 && p.push_ptr[d]) {
-        xdiff = (p.push_ptr[d] + (long long)z0 * p.push_slice[d] + (long long)y * p.push_pitch[d]) - pw[0];
-        xpush = true;
-      }
-    }
-  }
-
-  // mode 3: the edge lane parks its face cell of every plane in shared memory; after the march its warp writes the
-  // row's whole chunk (<= 32 planes = 256 bytes) into the neighbour's dense array with one coalesced store
-  __shared__ T xstage[PUSH == 3 ? 2 : 1][PUSH == 3 ? 8 : 1][PUSH == 3 ? 32 : 1];
-  int xside = -1;
-  if (PUSH == 3 && row_ok[0]) {
-    if (lane == 0 && x == p.lo[0] && p.push_ptr[0] && p.xdense[0]) xside = 0;
-    if (lane == 31 && x + VX == p.hi[0] && p.push_ptr[1] && p.xdense[1]) xside = 1;
-    if (xside >= 0) xpush = true;
-  }
-
-  // PUSH, y faces: the warp that owns the first (last) row of the subdomain stores it a second time, into the ghost row
-  // of the -y (+y) neighbour, with the same loop-invariant address difference (needs the neighbour's plane size to equal
-  // ours -- always true on a grid partition with equal x / y extents; otherwise the epilogue below does it).  Warp-uniform.
-  long long ydiff = 0;
-  bool ypush = false, yvec = false;
-  int ydir = -1;
-  if (PUSH && row_ok[0]) {
-    ydir = (y == p.lo[1]) ? 2 : ((y == p.hi[1] - 1) ? 3 : -1);
-    if (ydir == 2 && y == p.hi[1] - 1 && !p.push_ptr[2]) ydir = 3; // one-row subdomain: the loop serves one side
-    if (ydir >= 0 && p.push_ptr[ydir] && p.push_slice[ydir] == S) {
-      ydiff = (p.push_ptr[ydir] + (long long)x * (long long)sizeof(T) + (long long)z0 * S) - pw[0];
-      ypush = true;
-      yvec = ((unsigned long long)(pw[0] + ydiff) % sizeof(V)) == 0;
-    }
-  }
-
   V A[RY], B[RY], C[RY];
 #pragma unroll
   for (int j = 0; j < RY; ++j) {
@@ -270,29 +230,6 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
             if (cell_ok & (1u << i)) reinterpret_cast<T *>(pw[j])[i] = out.v[i];
         }
       }
-      if (PUSH) {
-        if (ypush) { // one warp in 512 rows
-          if (full && yvec) {
-            *reinterpret_cast<V *>(pw[j] + ydiff) = out;
-          } else {
-#pragma unroll
-            for (int i = 0; i < VX; ++i)
-              if (cell_ok & (1u << i)) reinterpret_cast<T *>(pw[j] + ydiff)[i] = out.v[i];
-          }
-        }
-      }
-      if (PUSH == 3) {
-        if (xpush) xstage[xside][warp][z - z0] = (xside == 0) ? out.v[0] : out.v[VX - 1];
-      }
-      if (PUSH == 1) {
-        if (xpush) { // two lanes per row
-          T v = out.v[0];
-#pragma unroll
-          for (int i = 1; i < VX; ++i)
-            if (x + i == p.lo[0] || x + i == p.hi[0] - 1) v = out.v[i];
-          *reinterpret_cast<T *>(pw[j] + xdiff) = v;
-        }
-      }
       pc[j] += S;
       ph[j] += (PUSH == 3) ? phstep : S;
       pw[j] += S;
@@ -310,53 +247,6 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
     step(C, A, B);
   }
 
-  if (PUSH == 3) {
-    // flush the staged x faces: warp-uniform (a warp belongs to one strip), one 8-byte element per lane and plane
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const int owner = side == 0 ? 0 : 31;
-      const bool mine = __shfl_sync(0xffffffffu, xside == side ? 1 : 0, owner) != 0;
-      if (!mine) continue;
-      __syncwarp();
-      if (lane < z1 - z0)
-        *reinterpret_cast<T *>(p.push_ptr[side] + (long long)y * p.push_pitch[side] + (long long)(z0 + lane) * (long long)sizeof(T)) = xstage[side][warp][lane];
-    }
-  }
-  if (PUSH) {
-    // Faces not served by the loop, after it: every lane re-reads the face cells IT stored in this chunk (its own
-    // writes: no barrier, L2-resident) and stores them into the ghost row / plane of the neighbour.  y: only a row
-    // whose neighbour has another plane size, or the second side of a one-row subdomain; z: the first / last chunk.
-    if (!row_ok[0] || !cell_ok) return;
-    const char *mine = p.dst + (long long)y * P + (long long)x * (long long)sizeof(T);
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const int dy = 2 + side;
-      if (!(side == 0 ? y == p.lo[1] : y == p.hi[1] - 1) || !p.push_ptr[dy] || (ypush && ydir == dy)) continue;
-      char *tgt = p.push_ptr[dy] + (long long)x * (long long)sizeof(T);
-#pragma unroll 8
-      for (int zz = z0; zz < z1; ++zz) {
-        const T *r = reinterpret_cast<const T *>(mine + (long long)zz * S);
-#pragma unroll
-        for (int i = 0; i < VX; ++i)
-          if (cell_ok & (1u << i)) reinterpret_cast<T *>(tgt + (long long)zz * p.push_slice[dy])[i] = r[i];
-      }
-    }
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const bool on = side == 0 ? (z0 == p.lo[2]) : (z1 == p.hi[2]);
-      if (!on || !p.push_ptr[4 + side]) continue;
-      const int zz = side == 0 ? z0 : z1 - 1;
-      char *tgt = p.push_ptr[4 + side] + (long long)y * p.push_pitch[4 + side] + (long long)x * (long long)sizeof(T);
-      const char *r = mine + (long long)zz * S;
-      if (full && ((unsigned long long)tgt % sizeof(V)) == 0 && ((unsigned long long)r % sizeof(V)) == 0) {
-        *reinterpret_cast<V *>(tgt) = *reinterpret_cast<const V *>(r);
-      } else {
-#pragma unroll
-        for (int i = 0; i < VX; ++i)
-          if (cell_ok & (1u << i)) reinterpret_cast<T *>(tgt)[i] = reinterpret_cast<const T *>(r)[i];
-      }
-    }
-  }
 }
 
 template <typename T, int VX, int RY, int MB, bool SHIFT>
@@ -367,98 +257,185 @@ __global__ void __launch_bounds__(256, MB) jacobi_march_kernel(const __grid_cons
   march_body<T, VX, RY, SHIFT, 0>(p, bx, b % tiles_y, b / tiles_y);
 }
 
-// Fused iteration (launch_jacobi_fused): the march over the WHOLE compute region with the halo exchange of the next
+// ---------------------------------------------------------------------------------------------------- fused iteration
+// launch_jacobi_fused: the march over the WHOLE compute region of a subdomain, with the halo exchange of the next
 // iteration and the ordering between ranks inside the kernel.
-//  * CTAs that touch no face of the subdomain ("inner": 64 % of them at 512^3) run the plain loop (PUSH = 0); the
-//    boundary CTAs run the push variant.  One kernel, one CTA-uniform branch.
-//  * order 1 / 2: the block index is remapped so that all boundary CTAs are dispatched first / last.  Boundary CTAs are
-//    the only ones that read ghost cells and the only ones that write into a neighbour, so they alone take part in the
-//    handshake: before the march a boundary CTA polls the mailbox slots of the neighbour ranks (ld.acquire.sys) until
-//    each has finished the previous iteration (its pushes have landed in my ghost cells AND it no longer reads the ghost
-//    cells I am about to overwrite); after the march it fences and counts itself in, and the last one to arrive stores
-//    the new iteration number into the neighbours' mailboxes (st.release.sys).  The inner CTAs (~230 us of work) absorb
-//    the skew between ranks, so no rank ever idles behind a separate wait / signal launch.
-template <typename T, int VX, bool SHIFT, int XM>
-__global__ void __launch_bounds__(256, 4)
-    jacobi_fused_kernel(const __grid_constant__ JacobiParams p, const __grid_constant__ FusedSync s, int nx, int ny, int nz) {
-  // boundary tiles: the first and the last along every axis (phase-shifted rows end one strip later than the others, so
-  // with SHIFT the last TWO strips along x may hold cells of the +x face)
-  const int xcols = min(nx, SHIFT ? 3 : 2), yrows = min(ny, 2), zslabs = min(nz, 2);
-  const int ix = nx - xcols, iy = ny - yrows, iz = nz - zslabs;
-  const int inner = ix * iy * iz;
-  int b = blockIdx.x;
-  int bx, by, bz;
-  bool edge;
-  if (s.order == 0) {
-    bx = b % nx;
-    b /= nx;
-    by = b % ny;
-    bz = b / ny;
-    edge = bx == 0 || bx >= nx - (xcols - 1) || by == 0 || by == ny - 1 || bz == 0 || bz == nz - 1;
-  } else {
-    const int nedge = nx * ny * nz - inner;
-    edge = s.order == 1 ? b < nedge : b >= inner;
-    if (!edge) {
-      const int j = s.order == 1 ? b - nedge : b;
-      bx = 1 + j % ix;
-      by = 1 + (j / ix) % iy;
-      bz = 1 + j / (ix * iy);
-    } else {
-      int k = s.order == 1 ? b : b - inner;
-      const int slab = nx * ny;
-      if (k < slab * zslabs) { // the -z slab, then the +z slab
-        bz = (k < slab) ? 0 : nz - 1;
-        k %= slab;
-        bx = k % nx;
-        by = k / nx;
-      } else { // rim of a middle plane: the -y row, the +y row, then the boundary strips of every middle row
-        k -= slab * zslabs;
-        const int rim = nx * yrows + iy * xcols;
-        bz = 1 + k / rim;
-        int r = k % rim;
-        if (r < nx * yrows) {
-          by = (r < nx) ? 0 : ny - 1;
-          bx = r % nx;
-        } else {
-          r -= nx * yrows;
-          by = 1 + r / xcols;
-          const int c = r % xcols;
-          bx = (c == 0) ? 0 : nx - xcols + c;
-        }
-      }
+//
+//  * Blocks run in the natural order (x fastest): measured, gathering the boundary CTAs at the start or the end of the
+//    grid costs 10 % (their 512-byte row segments lose the DRAM locality of whole rows).  CTAs that touch no face of the
+//    subdomain (64 % at 512^3) run the plain loop; boundary CTAs run the EDGE variant, which differs only in where the
+//    cells just outside the subdomain come from.  No push code inside any loop (it cost 36 % more issued instructions).
+//  * Face groups.  The cells of face f computed by one group of boundary CTAs form a slab of ~2048 cells that is shipped
+//    in one piece (struct Groups below): x faces -- 64 rows x zchunk planes of the column, y faces -- one strip of the row x
+//    zchunk planes, z faces -- 8 rows of the plane.  Every boundary CTA counts itself into the
+//    groups it belongs to (release at GPU scope); the LAST one to arrive re-reads the slab from dst (L2) and stores it
+//    into the neighbour -- ghost rows / planes, the ghost column, or the neighbour's dense x array -- then, if the
+//    neighbour is another rank, fences at system scope and publishes the iteration number in the neighbour's mailbox word
+//    for that group (st.release.sys).  ~220 of 8192 CTAs ship; only they pay an NVLink round trip.
+//  * Waiting.  Before marching, a boundary CTA polls the mailbox words of ITS groups (ld.acquire.sys, own memory) until
+//    the neighbour has shipped the previous iteration's slab: that one flag says both "the ghost cells I read are
+//    filled" and "the neighbour's group is done reading the ghost cells my group's shipper will overwrite".  Neighbours
+//    walk their grids in the same order, so the word a CTA needs was written a whole iteration earlier: x / y groups
+//    by construction, z groups because the z order is rotated by half the chunks (s.zrot) -- without the rotation the
+//    first chunk of iteration e+1 would need what the last chunk of iteration e ships.
+constexpr int kMaxGroups = SB_FUSED_MAX_GROUPS;
+
+// Group geometry (the same on both sides of a face: neighbours across a face have equal extents on the other two axes).
+// Slabs are kept to ~2048 cells so that the CTA that ships one reads it in one or two batches of independent loads:
+//   x face: group (z chunk, 8 tile rows)  = 64 rows x zchunk planes of the column,  members: the 8 (x nxhi) CTAs of those rows
+//   y face: group (z chunk, x tile)       = zchunk planes x one strip of the row,    members: 1
+//           (phase-shifted rows, SHIFT: strips of neighbouring rows do not line up -> one group per z chunk, members nx)
+//   z face: group (tile row)              = 8 rows x all x of the plane,             members: the nx CTAs of that tile row
+struct Groups {
+  int ny8; // x-face groups per z chunk
+  int nx;  // y-face groups per z chunk
+};
+template <bool SHIFT> __device__ __forceinline__ int group_of(int f, int bx, int by, int bz, const Groups &g) {
+  return f < 2 ? bz * g.ny8 + (by >> 3) : (f < 4 ? (SHIFT ? bz : bz * g.nx + bx) : by);
+}
+
+// all 256 threads: copy `total` cells; cell i is read from src_of(i) and stored to dst_of(i).  Eight independent loads per
+// thread are in flight before the first store (a shipper is the tail of its group: latency, not bandwidth, is what counts)
+template <typename T, typename SrcOf, typename DstOf> __device__ __forceinline__ void ship_cells(int total, SrcOf src_of, DstOf dst_of) {
+  for (int base = threadIdx.x; base < total; base += 256 * 8) {
+    T v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = base + k * 256;
+      if (i < total) v[k] = __ldcg(reinterpret_cast<const T *>(src_of(i)));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = base + k * 256;
+      if (i < total) *reinterpret_cast<T *>(dst_of(i)) = v[k];
     }
   }
-  if (!edge) {
+}
+
+// copy the slab of face f that belongs to the group of tile (bx, by, bz) from dst into the neighbour
+template <typename T, int VX, bool SHIFT> __device__ __forceinline__ void ship_face(const JacobiParams &p, int f, int bx, int by, int bz) {
+  const long long S = p.slice, P = p.pitch;
+  const long long es = (long long)sizeof(T);
+  const int z0 = p.lo[2] + bz * p.zchunk, z1 = min(z0 + p.zchunk, p.hi[2]);
+  if (f < 2) { // x face: column xc, the 64 rows of 8 tile rows, planes [z0, z1); consecutive threads along z (dense target: z fastest)
+    const int xc = f == 0 ? p.lo[0] : p.hi[0] - 1;
+    const int np = z1 - z0;
+    const int y0 = p.lo[1] + (by >> 3) * 64, rows = min(64, p.hi[1] - y0);
+    const char *src = p.dst + (long long)xc * es;
+    char *tgt = p.push_ptr[f];
+    const long long tp = p.push_pitch[f], ts = p.xdense[f] ? es : p.push_slice[f];
+    ship_cells<T>(
+        rows * np, [&](int i) { return src + (long long)(z0 + i % np) * S + (long long)(y0 + i / np) * P; },
+        [&](int i) { return tgt + (long long)(y0 + i / np) * tp + (long long)(z0 + i % np) * ts; });
+  } else if (f < 4) { // y face: row yf, planes [z0, z1), the cells of this x strip (SHIFT: the whole row)
+    const int yf = f == 2 ? p.lo[1] : p.hi[1] - 1;
+    const int xa = SHIFT ? p.lo[0] : max(p.lo[0], p.x0a + bx * 32 * VX), xb = SHIFT ? p.hi[0] : min(p.hi[0], p.x0a + (bx + 1) * 32 * VX);
+    const int ex = xb - xa;
+    if (ex <= 0) return;
+    const char *src = p.dst + (long long)yf * P + (long long)xa * es;
+    char *tgt = p.push_ptr[f] + (long long)xa * es;
+    const long long ts = p.push_slice[f];
+    ship_cells<T>(
+        ex * (z1 - z0), [&](int i) { return src + (long long)(z0 + i / ex) * S + (long long)(i % ex) * es; },
+        [&](int i) { return tgt + (long long)(z0 + i / ex) * ts + (long long)(i % ex) * es; });
+  } else { // z face: plane zf, the 8 rows of tile row `by`, all x
+    const int zf = f == 4 ? p.lo[2] : p.hi[2] - 1;
+    const int ex = p.hi[0] - p.lo[0];
+    const int y0 = p.lo[1] + by * 8, rows = min(8, p.hi[1] - y0);
+    const char *src = p.dst + (long long)zf * S + (long long)p.lo[0] * es;
+    char *tgt = p.push_ptr[f] + (long long)p.lo[0] * es;
+    const long long tp = p.push_pitch[f];
+    ship_cells<T>(
+        ex * rows, [&](int i) { return src + (long long)(y0 + i / ex) * P + (long long)(i % ex) * es; },
+        [&](int i) { return tgt + (long long)(y0 + i / ex) * tp + (long long)(i % ex) * es; });
+  }
+}
+
+template <typename T, int VX, bool SHIFT, int EDGE>
+__global__ void __launch_bounds__(256, 4)
+    jacobi_fused_kernel(const __grid_constant__ JacobiParams p, const __grid_constant__ FusedSync s, int nx, int ny, int nz) {
+  int b = blockIdx.x;
+  const int bx = b % nx;
+  b /= nx;
+  const int by = b % ny;
+  int bz = b / ny + s.zrot;
+  if (bz >= nz) bz -= nz;
+  const Groups g{(ny + 7) >> 3, nx};
+  // the faces this CTA's cells lie on (phase-shifted rows end one strip later than the others, so with SHIFT the last TWO
+  // strips along x may hold cells of the +x face); only faces with something to push form groups
+  const int nxhi = SHIFT ? min(nx, 2) : 1;
+  unsigned touch = 0;
+  if (bx == 0) touch |= 1u;
+  if (bx >= nx - nxhi) touch |= 2u;
+  if (by == 0) touch |= 4u;
+  if (by == ny - 1) touch |= 8u;
+  if (bz == 0) touch |= 16u;
+  if (bz == nz - 1) touch |= 32u;
+  if (!touch) {
     march_body<T, VX, 1, SHIFT, 0>(p, bx, by, bz);
     return;
   }
-  uint32_t epoch = 0;
-  if (s.n_wait > 0 || s.n_signal > 0) {
-    if (s.epoch) epoch = *reinterpret_cast<const volatile uint32_t *>(s.epoch);
-    if ((int)threadIdx.x < s.n_wait) {
-      const uint32_t want = s.wait_value + epoch;
+  unsigned faces = 0; // faces with a push
+#pragma unroll
+  for (int f = 0; f < 6; ++f)
+    if ((touch >> f & 1u) && p.push_ptr[f]) faces |= 1u << f;
+
+  if (s.any_wait && faces) {
+    const int f = threadIdx.x;
+    if (f < 6 && (faces >> f & 1u) && s.wait_row[f]) {
+      const uint32_t want = s.wait_value;
+      const uint32_t *slot = s.wait_row[f] + group_of<SHIFT>(f, bx, by, bz, g);
       uint32_t v;
       while (true) {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(s.wait_slot[threadIdx.x]) : "memory");
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
         if ((int32_t)(v - want) >= 0) break; // wrap-safe "v >= want"
-        __nanosleep(200);
+        __nanosleep(100);
       }
     }
     __syncthreads();
   }
-  march_body<T, VX, 1, SHIFT, XM>(p, bx, by, bz);
-  if (s.n_signal > 0) {
-    __syncthreads(); // every thread's pushes are issued ...
-    if (threadIdx.x == 0) {
-      __threadfence_system(); // ... and performed system-wide before this CTA counts itself in
-      if (atomicAdd(s.arrive, 1u) == (unsigned)(nx * ny * nz - inner) - 1u) {
-        __threadfence_system();
-        *s.arrive = 0; // the next launch starts from zero (stream order)
-        if (s.epoch) *s.epoch = epoch + 1;
-        const uint32_t value = s.signal_value + epoch;
-        for (int i = 0; i < s.n_signal; ++i) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.signal_slot[i]), "r"(value) : "memory");
+
+  march_body<T, VX, 1, SHIFT, EDGE>(p, bx, by, bz);
+  if (!faces) return;
+
+  __shared__ unsigned last_mask;
+  __syncthreads(); // every thread's stores to dst are issued ...
+  if (threadIdx.x == 0) {
+    __threadfence(); // ... and visible GPU-wide before this CTA counts itself in
+    unsigned m = 0;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+      if (!(faces >> f & 1u)) continue;
+      // x: the tile rows of this group (the last group may be short) x the strips holding the face; y: one strip; z: all strips
+      const unsigned members = f < 2 ? unsigned(min(8, ny - (by & ~7))) * (f == 1 ? unsigned(nxhi) : 1u) : (f < 4 && !SHIFT ? 1u : unsigned(nx));
+      uint32_t *cnt = s.counters + f * kMaxGroups + group_of<SHIFT>(f, bx, by, bz, g);
+      if (atomicAdd(cnt, 1u) == members - 1u) {
+        *cnt = 0; // the next launch on this stream starts from zero
+        m |= 1u << f;
       }
     }
+    if (m) __threadfence(); // acquire: the other members' stores
+    last_mask = m;
+  }
+  __syncthreads();
+  const unsigned mine = last_mask;
+  if (!mine) return;
+#pragma unroll
+  for (int f = 0; f < 6; ++f)
+    if (mine >> f & 1u) ship_face<T, VX, SHIFT>(p, f, bx, by, bz);
+  bool signal = false;
+#pragma unroll
+  for (int f = 0; f < 6; ++f)
+    if ((mine >> f & 1u) && s.signal_row[f]) signal = true;
+  if (!signal) return; // neighbours inside this process are ordered by stream events
+  __syncthreads();     // all of the slab is on its way ...
+  if (threadIdx.x == 0) {
+    __threadfence_system(); // ... and has landed in the neighbour before the flag does
+    const uint32_t value = s.signal_value;
+#pragma unroll
+    for (int f = 0; f < 6; ++f)
+      if ((mine >> f & 1u) && s.signal_row[f])
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.signal_row[f] + group_of<SHIFT>(f, bx, by, bz, g)), "r"(value) : "memory");
   }
 }
 
@@ -589,18 +566,22 @@ __global__ void __launch_bounds__(256) sqdiff_kernel(const char *a, const char *
 
 int env_int(const char *name, int dflt);
 
-template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p, const FusedSync &s, cudaStream_t stream) {
+template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p, FusedSync s, cudaStream_t stream) {
   const int x0a = p.x0a;
   const int tiles_x = (p.hi[0] - x0a + (SHIFT ? VX / 2 : 0) + 32 * VX - 1) / (32 * VX);
   const int ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
   const int tiles_z = (nz + p.zchunk - 1) / p.zchunk;
   const int tiles_y = (ny + 7) / 8;
+  if ((long long)tiles_z * ((tiles_y + 7) / 8) > kMaxGroups || (long long)tiles_z * tiles_x > kMaxGroups || tiles_y > kMaxGroups) return -2;
   const long long blocks = (long long)tiles_x * tiles_y * tiles_z;
-  if (p.xdense[0] || p.xdense[1] || p.xghost_ptr[0] || p.xghost_ptr[1])
+  // start in the middle of z when a z face waits for another rank (see the kernel's header)
+  s.zrot = (s.wait_row[4] || s.wait_row[5]) ? tiles_z / 2 : 0;
+  s.any_wait = 0;
+  for (int f = 0; f < 6; ++f)
+    if (s.wait_row[f]) s.any_wait = 1;
+  if (p.xghost_ptr[0] || p.xghost_ptr[1])
     jacobi_fused_kernel<T, VX, SHIFT, 3><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
-  else if (p.push_ptr[0] || p.push_ptr[1])
-    jacobi_fused_kernel<T, VX, SHIFT, 1><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
-  else // no x face to push (periodic self-neighbour read in place, or nothing asked)
+  else
     jacobi_fused_kernel<T, VX, SHIFT, 2><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
   return 1;
 }
@@ -741,6 +722,22 @@ static int pick_vectors(JacobiParams &p, int dtype_size, bool allow_shift, bool 
   return origin(1, 0);
 }
 
+// Arrival counters of the face groups: one zeroed block per (device, stream).  Launches on one stream are serialised and
+// every group's last arrival resets its counter, so the block is all zero again whenever the next launch starts.
+static uint32_t *group_counters(cudaStream_t stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, uint32_t *> pool;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  uint32_t *&c = pool[std::make_pair(dev, stream)];
+  if (!c) {
+    if (cudaMalloc(&c, 6 * kMaxGroups * sizeof(uint32_t)) != cudaSuccess) return nullptr;
+    cudaMemsetAsync(c, 0, 6 * kMaxGroups * sizeof(uint32_t), stream);
+  }
+  return c;
+}
+
 int launch_jacobi_fused(const JacobiParams &p_in, const FusedSync &sync_in, int dtype_size, cudaStream_t stream) {
   JacobiParams p = p_in;
   const int ex = p.hi[0] - p.lo[0], ey = p.hi[1] - p.lo[1], ez = p.hi[2] - p.lo[2];
@@ -752,10 +749,8 @@ int launch_jacobi_fused(const JacobiParams &p_in, const FusedSync &sync_in, int 
   if (p.zchunk > ez) p.zchunk = ez;
   p.prefetch = pf;
   FusedSync sync = sync_in;
-  if (sync.order < 0 || sync.order > 2) { // default: boundary CTAs first when ranks are ordered inside the kernel, natural order otherwise
-    const int order_env = env_int("SB_FUSED_ORDER", -1); // read per launch: tests switch it
-    sync.order = (order_env >= 0 && order_env <= 2) ? order_env : ((sync.n_wait > 0 || sync.n_signal > 0) ? 1 : 0);
-  }
+  if (!sync.counters) sync.counters = group_counters(stream);
+  if (!sync.counters) return -3;
   bool shift = false;
   const int vx = pick_vectors(p, dtype_size, allow_shift != 0, &shift);
   // x wrap (periodic self-neighbour read in place) works through the edge lanes' scalar load, so the first compute cell
@@ -763,9 +758,9 @@ int launch_jacobi_fused(const JacobiParams &p_in, const FusedSync &sync_in, int 
   // column is read by a vector load or a shuffle and the x faces are pushed into the ghost cells like any other face
   if (p.xwrap && !(!shift && p.x0a == p.lo[0] && (p.hi[0] - p.lo[0]) % (32 * vx) == 0)) p.xwrap = 0;
   if (p.xwrap) p.push_ptr[0] = p.push_ptr[1] = nullptr;
-  if (p.xdense[0] || p.xdense[1] || p.xghost_ptr[0] || p.xghost_ptr[1]) {
-    // dense x faces go through the edge lanes and a 32-plane shared-memory stage: same layout conditions as the wrap
-    if (shift || p.x0a != p.lo[0] || (p.hi[0] - p.lo[0]) % (32 * vx) != 0 || p.zchunk > 32) return -1;
+  if (p.xghost_ptr[0] || p.xghost_ptr[1]) {
+    // a dense received x array is read by the edge lanes' scalar load: same layout conditions as the wrap
+    if (shift || p.x0a != p.lo[0] || (p.hi[0] - p.lo[0]) % (32 * vx) != 0) return -1;
   }
   if (dtype_size == 8) {
     if (vx == 2) return shift ? launch_fused<double, 2, true>(p, sync, stream) : launch_fused<double, 2, false>(p, sync, stream);

@@ -44,15 +44,18 @@ struct JacobiParams {
   long long xghost_pitch[2];
 };
 
-// Ordering between ranks inside the fused kernel (see jacobi_fused_kernel).  All pointers are device addresses.
+// Face groups of the fused kernel (see jacobi_fused_kernel): at most this many z chunks / tile rows per subdomain
+#ifndef SB_FUSED_MAX_GROUPS
+#define SB_FUSED_MAX_GROUPS 1024
+#endif
+
+// Group counters and the ordering between ranks inside the fused kernel.  All pointers are device addresses.
 struct FusedSync {
-  const uint32_t *wait_slot[6]; // local mailbox slots, one per neighbour rank: proceed when (int32)(*slot - wait_value) >= 0
-  uint32_t *signal_slot[6];     // the neighbours' slots for this rank (peer / IPC mapped)
-  uint32_t *arrive;             // boundary-CTA counter (device, zero before the first launch; the kernel resets it)
-  uint32_t *epoch;              // optional device word added to both values and incremented by the kernel (graph replay)
-  int n_wait, n_signal;
+  uint32_t *counters;            // [6][SB_FUSED_MAX_GROUPS] arrival counters, zero between launches (null: the library's per-stream block)
+  const uint32_t *wait_row[6];   // per face: this GPU's mailbox row [group] written by the neighbour across that face (null: no wait)
+  uint32_t *signal_row[6];       // per face: the neighbour's mailbox row [group] for this subdomain (null: neighbour ordered by stream events)
   uint32_t wait_value, signal_value;
-  int order; // 0 natural block order, 1 boundary CTAs first, 2 boundary CTAs last, -1 default
+  int zrot, any_wait;            // set by the launcher
 };
 
 // Up to 8 thin regions (the exterior slabs of one subdomain) updated by ONE launch.

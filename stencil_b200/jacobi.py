@@ -242,118 +242,135 @@ class Jacobi3D:
         dd.swap()
 
     # ------------------------------------------------------------------ fused schedule
-    def _build_fused(self) -> None:
-        """Argument packs of sb_jacobi3d_fused per swap parity: the whole compute region + the six face neighbours'
-        output allocations (own memory, a peer GPU of this process, or another rank's IPC mapping)."""
+    def _build_fused(self) -> bool:
+        """Argument packs of sb_jacobi3d_fused_sync per swap parity: the whole compute region + the six face neighbours'
+        output allocations (own memory, a peer GPU of this process, or another rank's IPC mapping), the dense x arrays and
+        the mailboxes of the in-kernel handshake.  Returns False (on every rank alike) if the fused schedule does not
+        apply after all."""
         import os
 
+        from . import dist as _dist
+        from ._lib import FUSED_MAX_GROUPS, StepSync
         from .domain import CopyPlan, box_copy, get_neighbor
 
         dd, h = self.dd, self.h
         r = dd.radius_
-        dirs = ((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1))
-        # An x face is one 8-byte cell per row.  Pushed cell by cell into another GPU it costs 17 us per iteration through
-        # in-process peer access (fine) but 78 us through CUDA-IPC mappings; shipping a dense copy between kernels, or
-        # leaving the x faces to the copy engine between kernels, costs 30-70 us of serialised small launches (all
-        # measured on 2 x B200, profiles/README.md section 6.1).  Across ranks the x column therefore travels as 256-byte
-        # lines written by the kernel itself (below); where that is not possible or not validated the queued schedule
-        # runs instead.  One decision for the whole job: every rank evaluates the same partition.
+        dirs = FACE_DIRS
         part = dd.partition_
         es = dd.domains()[0].elem_size(h.id)
-        xmode = fused_x_mode(part, dd._owner, es, r, os.environ.get("SB_FUSED_IPC", ""))
-        x_crosses_ranks = xmode != "direct"
-        # x faces between ranks as dense [y][z] arrays: the kernel stages its column in shared memory and writes one
-        # 256-byte line per row and chunk into the neighbour's receive array (double buffered by swap parity); the
-        # neighbour's edge lanes read their x ghosts from that array (kernel mode 3, sb_halo_push.x_dense / x_recv).
-        dense = xmode == "dense" and all((d.pitched(h.id, w).ptr + r.x(-1) * es) % 16 == 0 for d in dd.domains() for w in ("curr", "next"))
-        if dd._remote is not None:
-            from . import dist as _dist
-
-            dense = all(_dist.all_gather_object(bool(dense)))
-        if x_crosses_ranks and not dense:  # the same on every rank (all-gathered)
-            return False
-        self._xbuf, self._xopened = [], []
-        recv, remote_recv = {}, {}
         L = lib()
-        if dense:
-            from . import dist as _dist
+        me = dd._world.rank
+        multi_rank = dd._remote is not None
 
+        def gather(obj):
+            return _dist.all_gather_object(obj) if multi_rank else [obj]
+
+        # An x face is one cell per row: 8 bytes every 4112.  Stored cell by cell into another GPU it is one tiny NVLink
+        # transaction per row (78 us per iteration through CUDA-IPC mappings, profiles/README.md section 6.1), so towards
+        # any OTHER subdomain the column travels as a dense [y][z] array (z fastest, like the march): the shipping CTA
+        # writes 256-byte lines into the neighbour's receive array (double buffered by swap parity) and the neighbour's
+        # edge lanes read their x ghosts from it.  Needs whole warp strips along x and a 16-byte aligned first compute
+        # cell; otherwise the column goes into the ghost column (inside a process) or the schedule is "queued" (across
+        # ranks, decided by fused_schedule).  One decision for the whole job: every rank evaluates the same inputs.
+        strip = 32 * (16 // es)
+        layout = all(part.subdomain_size(i)[0] % strip == 0 and ((part.subdomain_size(i)[0] + r.x(-1) + r.x(1)) * es) % 16 == 0 for i in part.indices())
+        aligned = all((d.pitched(h.id, w).ptr + r.x(-1) * es) % 16 == 0 for d in dd.domains() for w in ("curr", "next"))
+        dense = layout and all(gather(bool(aligned)))
+        x_crosses_ranks = fused_x_mode(part, dd._owner, es, r, os.environ.get("SB_FUSED_IPC", "")) != "direct"
+        if x_crosses_ranks and not dense:
+            return False
+
+        self._xbuf, self._xopened = [], []
+
+        def dev_alloc(nbytes, gpu):
+            pbuf = C.c_void_p()
+            check(L.sb_malloc(C.byref(pbuf), nbytes, gpu))
+            check(L.sb_memset(pbuf, 0, nbytes, gpu, None))
+            self._xbuf.append((int(pbuf.value), gpu))
+            return int(pbuf.value)
+
+        def export(ptr):
+            hb = (C.c_char * 64)()
+            check(L.sb_ipc_export(C.c_void_p(ptr), hb))
+            return bytes(hb)
+
+        def nbr_of(di, k):
+            idx = tuple(dd.domain_idx_[di])
+            nidx = tuple(get_neighbor(idx, dirs[k], part.dim))
+            return idx, nidx, dd._owner[nidx]
+
+        # receive arrays: one per local subdomain, x side and swap parity, where the x neighbour is another subdomain
+        recv = {}
+        if dense:
             for di, d in enumerate(dd.domains()):
-                idx = tuple(dd.domain_idx_[di])
                 raw = d.raw_size()
-                for side, dv in enumerate(dirs[:2]):
-                    nidx = tuple(get_neighbor(idx, dv, part.dim))
-                    if dd._owner[nidx][0] == dd._world.rank:
-                        continue
-                    bufs = []
-                    for _ in range(2):  # one receive array per swap parity
-                        pbuf = C.c_void_p()
-                        check(L.sb_malloc(C.byref(pbuf), raw[1] * raw[2] * es, d.gpu()))
-                        check(L.sb_memset(pbuf, 0, raw[1] * raw[2] * es, d.gpu(), None))
-                        bufs.append(int(pbuf.value))
-                        self._xbuf.append((int(pbuf.value), d.gpu()))
-                    recv[(di, side)] = bufs
-            mine = {}
-            for (di, side), ptrs in recv.items():
-                handles = []
-                for ptr in ptrs:
-                    hb = (C.c_char * 64)()
-                    check(L.sb_ipc_export(C.c_void_p(ptr), hb))
-                    handles.append(bytes(hb))
-                mine[(tuple(dd.domain_idx_[di]), side)] = handles
+                for side in (0, 1):
+                    idx, nidx, _ = nbr_of(di, side)
+                    if nidx != idx:
+                        recv[(idx, side)] = [dev_alloc(raw[1] * raw[2] * es, d.gpu()) for _ in range(2)]
+        # mailboxes of the in-kernel handshake: one subdomain per rank (the torchrun layout) with neighbours on other ranks
+        inkernel = multi_rank and len(dd.domains()) == 1 and os.environ.get("SB_FUSED_INKERNEL", "1") != "0"
+        mailbox = dev_alloc(6 * FUSED_MAX_GROUPS * 4, dd.domains()[0].gpu()) if inkernel else 0
+        for _, gpu in self._xbuf:
+            check(L.sb_device_sync(gpu))
+        remote_recv, remote_mail = {}, {}
+        if multi_rank:
+            mine = {"recv": {key: [export(p_) for p_ in ptrs] for key, ptrs in recv.items()}, "mail": export(mailbox) if mailbox else None}
             wanted = set()  # the receive arrays my subdomains write into: side 1 - s of my neighbour on side s
             for di in range(len(dd.domains())):
-                idx = tuple(dd.domain_idx_[di])
-                for s_, dv in enumerate(dirs[:2]):
-                    nidx = tuple(get_neighbor(idx, dv, part.dim))
-                    if dd._owner[nidx][0] != dd._world.rank:
+                for s_ in (0, 1):
+                    idx, nidx, (nrank, _) = nbr_of(di, s_)
+                    if nrank != me:
                         wanted.add((nidx, 1 - s_))
-            for rank, table in enumerate(_dist.all_gather_object(mine)):
-                if rank == dd._world.rank:
+            nbr_ranks = {nbr_of(di, k)[2][0] for di in range(len(dd.domains())) for k in range(6)} - {me}
+            gpu0 = dd.domains()[0].gpu()
+
+            def open_(hnd):
+                out = C.c_void_p()
+                check(L.sb_ipc_import(hnd, gpu0, C.byref(out)))
+                self._xopened.append(int(out.value))
+                return int(out.value)
+
+            for rank, table in enumerate(gather(mine)):
+                if rank == me:
                     continue
-                for key, handles in table.items():
+                for key, handles in table["recv"].items():
                     key = (tuple(key[0]), key[1])
-                    if key not in wanted:
-                        continue
-                    ptrs = []
-                    for hnd in handles:
-                        out = C.c_void_p()
-                        check(L.sb_ipc_import(hnd, dd.domains()[0].gpu(), C.byref(out)))
-                        self._xopened.append(int(out.value))
-                        ptrs.append(int(out.value))
-                    remote_recv[key] = ptrs
+                    if key in wanted:
+                        remote_recv[key] = [open_(hnd) for hnd in handles]
+                if inkernel and rank in nbr_ranks and table["mail"] is not None:
+                    remote_mail[rank] = open_(table["mail"])
+
         self._fused_calls, self._init_plans = [], []
         self._fused_nbr_slots = []  # in-process neighbours of each local subdomain (stream dependencies)
         for rel in (0, 1):
             absolute = (self._parity0 + rel) & 1
             per_dom, inits = [], []
             for di, d in enumerate(dd.domains()):
-                idx = tuple(dd.domain_idx_[di])
                 src = d.pitched(h.id, "curr" if rel == 0 else "next")
                 dst = d.pitched(h.id, "next" if rel == 0 else "curr")
                 push = HaloPush()
                 slots = set()
                 init_copies = []
-                for k, dv in enumerate(dirs):
-                    nidx = get_neighbor(idx, dv, dd.partition_.dim)
+                myraw = d.raw_size()
+                for k in range(6):
+                    idx, nidx, (rank, slot) = nbr_of(di, k)
                     # the neighbour's NEXT buffer at this parity is its curr buffer of the other parity
                     pn, _ = dd._pitched_of(nidx, h.id, absolute ^ 1)
-                    rank, slot = dd._owner[tuple(nidx)]
-                    if rank == dd._world.rank:
+                    if rank == me:
                         raw = dd.domains_[slot].raw_size()
                         slots.add(slot)
                     else:
                         raw = dd._remote.raw_of(nidx)
                     push.nbr[k] = Pitched(pn.ptr, pn.pitch, pn.ysize)
                     push.nbr_zsize[k] = raw[2]
-                    if k < 2 and dense and rank != dd._world.rank:
-                        myraw = d.raw_size()
-                        target = remote_recv[(tuple(nidx), 1 - k)]
+                    if k < 2 and (idx, k) in recv:
+                        target = recv[(nidx, 1 - k)] if rank == me else remote_recv[(nidx, 1 - k)]
                         # iteration `rel` writes what the neighbour reads in the next one (parity rel ^ 1)
                         push.nbr[k] = Pitched(target[rel ^ 1], es, myraw[1])
                         push.nbr_zsize[k] = myraw[2]
                         push.x_dense[k] = 1
-                        push.x_recv[k] = recv[(di, k)][rel]
+                        push.x_recv[k] = recv[(idx, k)][rel]
                         # before the first fused iteration at this parity: the neighbour needs my column of curr itself
                         lo3 = (r.x(-1), r.y(-1), r.z(-1))
                         sz3 = d.size()
@@ -372,34 +389,24 @@ class Jacobi3D:
                     self._fused_nbr_slots.append(sorted(slots))
             self._fused_calls.append(per_dom)
             self._init_plans.append(inits)
-        self._fn_fused = lib().sb_jacobi3d_fused_sync
+        self._fn_fused = L.sb_jacobi3d_fused_sync
         self._fused_epoch = 0
         self._ev_fused = None
         self._ghosts_current = False
-        # Ordering between ranks.  One subdomain per rank (the torchrun layout): inside the kernel -- its boundary CTAs
-        # poll the face-neighbour ranks' counters and the last one signals (sb_jacobi3d_fused_sync); no extra launch.
-        # Several subdomains per rank: one counter per rank, signalled by a tiny kernel after all of them (sb_signal).
+        # Ordering between ranks.  One subdomain per rank: inside the kernel -- boundary CTAs poll the mailbox word of
+        # their face group, the CTA that ships a group's slab publishes the iteration number in the neighbour's mailbox
+        # (sb_jacobi3d_fused_sync); no extra launch.  Several subdomains per rank: one counter per rank, signalled by a tiny
+        # kernel after all of them (dist.RemoteDomains.signal_step / wait_step).
         self._sync = None
-        if dd._remote is not None and len(dd.domains()) == 1 and os.environ.get("SB_FUSED_INKERNEL", "1") != "0":
-            idx = tuple(dd.domain_idx_[0])
-            ranks = sorted({dd._owner[tuple(get_neighbor(idx, dv, part.dim))][0] for dv in dirs} - {dd._world.rank})
-            if ranks:
-                from ._lib import StepSync
-
-                parr = C.c_void_p()
-                check(L.sb_malloc(C.byref(parr), 4, dd.domains()[0].gpu()))
-                check(L.sb_memset(parr, 0, 4, dd.domains()[0].gpu(), None))
-                check(L.sb_device_sync(dd.domains()[0].gpu()))
-                self._arrive = int(parr.value)
-                mine, theirs = dd._remote.step_slots(ranks)
-                sy = StepSync()
-                for i, (a, b) in enumerate(zip(mine, theirs)):
-                    sy.wait_slots[i], sy.signal_slots[i] = a, b
-                sy.n_wait = sy.n_signal = len(ranks)
-                sy.arrive = self._arrive
-                sy.epoch = None
-                sy.order = int(os.environ.get("SB_FUSED_ORDER", "-1"))
-                self._sync = sy
+        if inkernel and remote_mail:
+            sy = StepSync()
+            row = FUSED_MAX_GROUPS * 4
+            for k in range(6):
+                _, _, (rank, _) = nbr_of(0, k)
+                if rank != me:
+                    sy.wait_rows[k] = mailbox + k * row  # written by the neighbour across face k ...
+                    sy.signal_rows[k] = remote_mail[rank] + (k ^ 1) * row  # ... which sees me across its face k ^ 1
+            self._sync = sy
         return True
 
     def step_fused(self, timing=None) -> None:
@@ -453,9 +460,9 @@ class Jacobi3D:
                     if sj != di:
                         s.wait_event(prev[sj])
             sync = self._sync
-            if sync is not None:  # iteration e waits for e and signals e + 1, inside the kernel
-                sync.wait_value = remote.step_epoch & 0xFFFFFFFF
-                sync.signal_value = (remote.step_epoch + 1) & 0xFFFFFFFF
+            if sync is not None:  # iteration e (of this object: its mailboxes start at zero) waits for e and signals e + 1
+                sync.wait_value = self._fused_epoch & 0xFFFFFFFF
+                sync.signal_value = (self._fused_epoch + 1) & 0xFFFFFFFF
             elif remote is not None:
                 remote.wait_step(remote.step_epoch, s)
             if timing is not None and di == 0:
@@ -479,27 +486,30 @@ class Jacobi3D:
         dd.swap()
 
     def close(self) -> None:
-        """Drain the queued work; release the dense x receive arrays of the SB_FUSED_IPC experiment."""
+        """Drain the queued work; release the dense x receive arrays and mailboxes of the fused schedule."""
         self.synchronize()
-        if getattr(self, "_arrive", None):
-            lib().sb_free(C.c_void_p(self._arrive), self.dd.domains()[0].gpu())
-            self._arrive, self._sync = None, None
+        self._sync = None
         if not getattr(self, "_xbuf", None) and not getattr(self, "_xopened", None):
             return
-        import torch.distributed as td
-
+        multi_rank = self.dd._remote is not None
+        if multi_rank:
+            import torch.distributed as td
         for plans in getattr(self, "_init_plans", []):
             for p in plans:
                 if p is not None:
                     p.destroy()
         self._init_plans = []
-        td.barrier()  # nobody unmaps or frees while a neighbour could still write
+        if multi_rank:
+            td.barrier()  # nobody unmaps or frees while a neighbour could still write
         for ptr in self._xopened:
             lib().sb_ipc_close(C.c_void_p(ptr), self.dd.domains()[0].gpu())
-        td.barrier()
+        if multi_rank:
+            td.barrier()
         for ptr, dev in self._xbuf:
             lib().sb_free(C.c_void_p(ptr), dev)
         self._xbuf, self._xopened = [], []
+        if hasattr(self, "_fused_calls"):
+            del self._fused_calls  # a later step_fused() builds everything again
 
     def synchronize(self) -> None:
         """Wait for the compute streams (bin/jacobi3d.cu:363-365)."""

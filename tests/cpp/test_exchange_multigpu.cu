@@ -1,4 +1,5 @@
-// C++ API check on ALL visible GPUs (1 process x N GPUs): fill every subdomain's compute region with a
+// C++ API check on ALL visible GPUs -- 1 process x N GPUs, or one rank per GPU under bin/sb_mpirun -n N (every rank
+// checks its own subdomains; the verdict is all-reduced): fill every subdomain's compute region with a
 // function of the global coordinate, exchange (+ swap + exchange again), and verify that the WHOLE
 // allocation of every quantity -- ghost cells included -- holds the periodically wrapped function.
 // This is the check of the reference's test/test_exchange.cu:153-187 extended to several GPUs, several
@@ -74,8 +75,12 @@ static long run_case(size_t X, size_t Y, size_t Z, const Radius &radius, const c
     }
     dd.swap(); // the next round fills and exchanges the other buffer
   }
-  std::printf("%-28s %zux%zux%zu on %zu subdomains: %s (%ld mismatches)\n", name, X, Y, Z, dd.domains().size(), bad ? "FAIL" : "ok", bad);
-  return bad;
+  long long all = bad;
+  MPI_Allreduce(MPI_IN_PLACE, &all, 1, MPI_LONG_LONG, MPI_SUM, MPI_COMM_WORLD);
+  if (0 == mpi::world_rank())
+    std::printf("%-28s %zux%zux%zu on %d rank(s) x %zu subdomain(s): %s (%lld mismatches)\n", name, X, Y, Z, mpi::world_size(), dd.domains().size(),
+                all ? "FAIL" : "ok", all);
+  return long(all);
 }
 
 int main(int argc, char **argv) {
@@ -91,7 +96,7 @@ int main(int argc, char **argv) {
     bad += run_case(48, 40, 32, r, "asymmetric +x2 -y3");
   }
   bad += run_case(128, 128, 128, Radius::face_edge_corner(1, 0, 0), "jacobi faces r=1");
+  if (0 == mpi::world_rank()) std::printf(bad ? "FAILED\n" : "ALL OK\n");
   MPI_Finalize();
-  std::printf(bad ? "FAILED\n" : "ALL OK\n");
   return bad ? 1 : 0;
 }

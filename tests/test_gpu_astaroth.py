@@ -51,7 +51,7 @@ BOXES = [
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("variant", [ac.AUTO, ac.CELL, ac.TILE])
+@pytest.mark.parametrize("variant", [ac.AUTO, ac.CELL, ac.TILE, ac.TEAM])
 @pytest.mark.parametrize("box", BOXES, ids=[f"{b[0]}-{b[1]}-{b[2]}" for b in BOXES])
 def test_substeps_match_oracle(dtype, variant, box):
     raw, lo, hi = box
@@ -72,7 +72,7 @@ def test_substeps_match_oracle(dtype, variant, box):
         assert np.array_equal(a[m], b[m])
 
 
-@pytest.mark.parametrize("variant", [ac.CELL, ac.TILE])
+@pytest.mark.parametrize("variant", [ac.CELL, ac.TILE, ac.TEAM])
 @pytest.mark.parametrize("shape", [0, 1])
 def test_tile_shapes_and_zchunks(variant, shape, monkeypatch):
     """Both tile shapes per precision (SB_AC_SHAPE) and a forced short z chunk (ring warm-up at every chunk start)."""
@@ -89,7 +89,7 @@ def test_tile_shapes_and_zchunks(variant, shape, monkeypatch):
 
 
 @pytest.mark.skipif(not os.path.exists(GOLDEN), reason="golden vectors not generated yet (oracle/ref/make_astaroth_golden.py)")
-@pytest.mark.parametrize("variant", [ac.CELL, ac.TILE])
+@pytest.mark.parametrize("variant", [ac.CELL, ac.TILE, ac.TEAM])
 def test_matches_reference_kernel_golden(variant):
     """The reference's own solve<0,1,2> (astaroth/kernels.cu, compiled unmodified for sm_100a) produced these."""
     z = np.load(GOLDEN)

@@ -271,3 +271,38 @@ def test_fused_kernel_block_orders(monkeypatch, order, dtype):
                 dd.close()
         for a, b in zip(*fields):
             assert np.array_equal(a, b), (size, ndom)
+
+
+@pytest.mark.parametrize("schedule", ["host-sync", "queued", "fused"])
+def test_jacobi_vs_reference_kernel_golden(schedule):
+    """The CUDA kernels (all three schedules, FP32 = the reference's dtype) against the reference's own stencil_kernel run
+    on a B200 (tests/golden/jacobi_ref.npz): bit for bit against its IEEE build, one ulp per iteration against its
+    --use_fast_math build (approximate divide, bin/CMakeLists.txt:56)."""
+    import os
+
+    from stencil_b200.jacobi import Jacobi3D, jacobi_radius
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jacobi_ref.npz"))
+    iters = [int(i) for i in gold["iters"]]
+    for si, shape in enumerate(gold["shapes"]):
+        shape = tuple(int(v) for v in shape)
+        dd = sb.DistributedDomain(*shape)
+        dd.set_gpus([0])
+        dd.set_radius(jacobi_radius())
+        h = dd.add_data(np.float32, "d")
+        dd.realize()
+        try:
+            jac = Jacobi3D(dd, h)
+            jac.init(0.5)
+            done = 0
+            for k, target in enumerate(iters):
+                while done < target:
+                    {"host-sync": jac.step, "queued": jac.step_async, "fused": jac.step_fused}[schedule]()
+                    done += 1
+                jac.synchronize()
+                got = dd.domains()[0].interior_to_host(0)
+                ieee, fast = gold[f"ieee_{si}"][k], gold[f"fast_{si}"][k]
+                assert np.array_equal(got, ieee), (shape, target, int(np.count_nonzero(got != ieee)))
+                assert float(np.abs(got.astype(np.float64) - fast).max()) <= 6e-8 * target + 1e-12  # <= 1 ulp per iteration (fast divide)
+        finally:
+            dd.close()
