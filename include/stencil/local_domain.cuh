@@ -42,6 +42,7 @@ class LocalDomain {
 
   std::vector<cudaPitchedPtr> currDataPtrs_;
   std::vector<cudaPitchedPtr> nextDataPtrs_;
+  std::vector<void *> allocBases_; // what cudaMalloc returned for every allocation above (freed by the destructor)
   std::vector<size_t> dataElemSize_;
   std::vector<std::string> dataName_;
 
@@ -61,6 +62,11 @@ class LocalDomain {
 public:
   LocalDomain(Dim3 sz, Dim3 origin, int dev);
   ~LocalDomain();
+  // Copies share nothing: a LocalDomain may only be copied BEFORE realize() (DistributedDomain fills its vector that way,
+  // like the reference, src/stencil.cu:261-267); copying one that owns device memory would free it twice.
+  LocalDomain(const LocalDomain &o);
+  LocalDomain &operator=(const LocalDomain &) = delete;
+  LocalDomain(LocalDomain &&o) noexcept;
 
   void set_device(CudaErrorsFatal fatal = CudaErrorsFatal::YES);
 

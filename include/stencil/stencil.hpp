@@ -63,6 +63,7 @@ private:
 
   Method flags_;
   PlacementStrategy strategy_;
+  Topology::Boundary boundary_; // PERIODIC (the reference's only kind) or FIXED
 
   // the fused exchange: plans_[parity][local domain]; parity = number of swap() calls mod 2.
   // Phase 1 (plans_): each subdomain stores its outgoing halos into the neighbours' ghost cells -- except
@@ -150,6 +151,9 @@ public:
   // choose transports (before realize):  d.set_methods(Method::CudaMpi | Method::CudaKernel);
   void set_methods(Method flags) noexcept;
   void set_placement(PlacementStrategy strategy) noexcept { strategy_ = strategy; }
+  // how the grid closes at its faces (before realize).  PERIODIC is the reference's behaviour; FIXED plans no messages
+  // across the faces of the whole grid (the ghost cells there keep what the application put into them)
+  void set_boundary(Topology::Boundary boundary) noexcept { boundary_ = boundary; }
   bool any_methods(Method methods) const noexcept { return methods && flags_; }
   // CUDA devices for this rank (before realize); repeats are allowed (several subdomains per GPU)
   void set_gpus(const std::vector<int> &cudaIds) { gpus_ = cudaIds; }

@@ -1,7 +1,9 @@
 #pragma once
 // The grid of subdomains as a graph: Topology::get_neighbor(index, dir) answers "which subdomain lies one step in
-// direction dir (each component -1, 0 or +1) from subdomain `index`?".  Only periodic grids exist (as in the
-// reference, topology.hpp:12-15), so the answer always exists; OptionalNeighbor keeps the reference's two fields.
+// direction dir (each component -1, 0 or +1) from subdomain `index`?".  The reference only has periodic grids
+// (topology.hpp:12-15: `enum Boundary { NONE, PERIODIC }`, boundary.hpp is a stub); FIXED is this library's addition: the
+// grid ends at its faces, a step across one has no neighbour (OptionalNeighbor::exists == false), no message is planned
+// for it and the ghost cells on a physical boundary are the application's to fill.
 
 #include <cassert>
 
@@ -10,7 +12,7 @@
 
 class Topology {
 public:
-  enum class Boundary { NONE, PERIODIC };
+  enum class Boundary { NONE, PERIODIC, FIXED };
 
   struct OptionalNeighbor {
     Dim3 index;

@@ -144,7 +144,8 @@ int sb_jacobi3d_regions(sb_pitched dst, sb_pitched src, int dtype_size, const in
  * step 0..2 = Williamson RK3 substep; step 0 ignores the previous contents of `out`.
  * params: the uniforms solve<> reads through DCONST (acDeviceLoadMeshInfo / acDeviceLoadScalarUniform,
  * astaroth/kernels.cu:89-163).  variant: 0 auto, 1 cell kernel, 2 tile kernel (one thread per cell), 3 team kernel (two specialised
- * threads per cell on the same shared-memory ring).
+ * threads per cell on the same shared-memory ring; FP64: ring fed by TMA when the buffers allow it), 4 / 5 the TMA-fed
+ * two- / three-team kernel or an error.
  * dtype_size 8 = double (the reference's AcReal), 4 = float.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -183,18 +184,17 @@ int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int6
 /* The same launch with the ordering BETWEEN RANKS inside the kernel, replacing the reference's per-iteration host
  * synchronisation (DistributedDomain::exchange() returns after MPI_Waitall / stream syncs, src/stencil.cu:1120-1186;
  * bin/jacobi3d.cu:337-365) and this library's own sb_wait / sb_signal launches.
- * The kernel ships every face in GROUPS of ~2048 cells (x faces: 64 rows x one z chunk of 32 planes of the column; y faces:
- * one 32-lane strip of the row x one z chunk; z faces: 8 rows of the plane -- the index arithmetic is the kernel's, the same
- * on both sides of a face); the last CTA of a group stores the slab into the neighbour, fences at system scope and
- * writes signal_value into signal_rows[f][group] -- a uint32 array of SB_FUSED_MAX_GROUPS words in the NEIGHBOUR's memory
+ * Every boundary tile of the kernel (256 threads: one 32-lane strip x 8 rows x one z chunk of 32 planes) ships its own face
+ * cells into the neighbour after its march, fences at system scope and
+ * writes signal_value into signal_rows[f][tile] -- a uint32 array of SB_FUSED_MAX_GROUPS words in the NEIGHBOUR's memory
  * (peer / IPC mapped): its mailbox row for the face it shares with this subdomain.  Before marching, a CTA on face f polls
- * wait_rows[f][group] (this GPU's own mailbox row for face f, written by the neighbour across f; ld.acquire.sys) until
+ * wait_rows[f][tile] (this GPU's own mailbox row for face f, written by the neighbour across f; relaxed loads + one fence) until
  * (int32)(word - wait_value) >= 0.  Protocol: iteration e waits for e and signals e + 1 -- a neighbour that has shipped
- * group g of iteration e - 1 has (a) filled the ghost cells iteration e reads there and (b) stopped reading the ghost cells
+ * tile t of iteration e - 1 has (a) filled the ghost cells iteration e reads there and (b) stopped reading the ghost cells
  * iteration e overwrites there.  Neighbours walk their grids in the same order, so in steady state every word was written
  * an iteration earlier and nobody spins.  Faces: -x,+x,-y,+y,-z,+z.  NULL rows: no wait / no signal on that face
  * (neighbour in the same process: order the launches with stream events).  sync == NULL: no handshake at all. */
-#define SB_FUSED_MAX_GROUPS 1024
+#define SB_FUSED_MAX_GROUPS 4096
 typedef struct {
   const uint32_t *wait_rows[6];
   uint32_t *signal_rows[6];

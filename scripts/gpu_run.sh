@@ -38,9 +38,9 @@ for stage in "$@"; do
   tests) # the whole GPU suite
     timeout 1700 python -m pytest tests -q -m gpu -x 2>&1 | tail -8 | tee "$F/pytest_gpu.txt" ;;
   tests_jacobi)
-    timeout 900 python -m pytest tests/test_gpu_jacobi.py -q -m gpu -x 2>&1 | tail -8 | tee "$F/pytest_jacobi.txt" ;;
-  tests_mp) # multi-rank parity (needs N >= 2)
-    timeout 900 python -m pytest tests/test_gpu_exchange.py -q -m gpu -x -k "one_process or multi_gpu" 2>&1 | tail -8 | tee "$F/pytest_mp.txt" ;;
+    timeout 900 python -m pytest tests/test_gpu_jacobi.py -q -m gpu -x 2>&1 | tail -40 | tee "$F/pytest_jacobi.txt" | cut -c1-250 ;;
+  tests_mp) # multi-rank / multi-GPU parity (python one-process-per-GPU + in-process, C++ ranks under sb_mpirun)
+    timeout 900 python -m pytest tests/test_gpu_exchange.py tests/test_gpu_cpp_api.py -q -m gpu -x -k "one_process or multi_gpu or multi_rank or one_rank_per_gpu" 2>&1 | tail -8 | tee "$F/pytest_mp.txt" ;;
   mp_check) # the torchrun parity script itself, with its per-shape lines
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29861 tests/mp_exchange_check.py 2>"$F/mp_check.err" | tee "$F/mp_check.txt" | cut -c1-400
     tail -5 "$F/mp_check.err" | cut -c1-400 ;;
@@ -56,6 +56,18 @@ for stage in "$@"; do
     bench f32 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --dtype f32 ;;
   bench_queued)
     bench queued --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --schedule queued --no-parity ;;
+  bench_diag) # where the multi-rank overhead of the fused kernel goes (timing only: some of these compute wrong halos)
+    SB_FUSED_REGS=64 bench regs64 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
+    SB_DEBUG_FUSED=1 bench nowait --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
+    SB_DEBUG_FUSED=3 bench nowait_nosignal --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
+    SB_DEBUG_NOPUSH=1 bench nopush --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity ;;
+  time_fused) # kernel variants + single-GPU stand-ins for the multi-rank kernels, one box
+    timeout 900 python scripts/time_fused.py 512 30 2>&1 | tail -24 | tee "$F/time_fused.txt" ;;
+  ncu_fused2) # the fused kernel of the 2-subdomain stand-in (half of its CTAs are boundary CTAs) under ncu
+    ONLY=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:jacobi_fused -s 12 -c 2 -o "$F/prof_jacobi_fused2" -f python scripts/time_fused.py 512 4 >"$F/ncu_fused2.log" 2>&1
+    tail -3 "$F/ncu_fused2.log" ;;
+  tests_astaroth)
+    timeout 900 python -m pytest tests/test_gpu_astaroth.py -q -m gpu -x 2>&1 | tail -60 | tee "$F/pytest_astaroth.txt" | cut -c1-250 ;;
   bench_launchsync) # the round-1 handshake (separate wait / signal launches) for the before/after
     SB_FUSED_INKERNEL=0 bench launchsync --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity ;;
   bench_reference)
@@ -77,8 +89,8 @@ for stage in "$@"; do
   golden) # reference-generated golden vectors (oracle/ref/*.py), written to gpurun_out/
     timeout 300 python oracle/ref/make_jacobi_golden.py 2>&1 | tail -8 ;;
   astaroth)
-    SKIP_CELL=1 timeout 300 python scripts/time_astaroth.py 256 f64 5 2>&1 | tail -6 | tee "$F/astaroth_f64.txt"
-    SKIP_CELL=1 timeout 300 python scripts/time_astaroth.py 256 f32 5 2>&1 | tail -6 | tee "$F/astaroth_f32.txt" ;;
+    SKIP_CELL=1 timeout 300 python scripts/time_astaroth.py 256 f64 5 2>&1 | tail -16 | tee "$F/astaroth_f64.txt"
+    SKIP_CELL=1 timeout 300 python scripts/time_astaroth.py 256 f32 5 2>&1 | tail -10 | tee "$F/astaroth_f32.txt" ;;
   *) # anything else: a script path with arguments in SB_ARGS
     if [ -f "$stage" ]; then timeout 900 bash "$stage" 2>&1 | tail -40 | tee "$F/$(basename "$stage").txt"; else echo "unknown stage $stage"; fi ;;
   esac

@@ -47,7 +47,9 @@ def timeit(fn, reps=reps):
 
 
 tag = os.environ.get("SB_AC_SHAPE", "0") + "/" + os.environ.get("SB_AC_ZCHUNK", "auto")
-for variant, name in ((ac.TEAM, "team"), (ac.TILE, "tile"), (ac.CELL, "cell")):
+for variant, name in ((ac.TEAM3_TMA, "team3-tma"), (ac.TEAM_TMA, "team2-tma"), (ac.TEAM, "team"), (ac.TILE, "tile"), (ac.CELL, "cell")):
+    if variant in (ac.TEAM3_TMA, ac.TEAM_TMA) and dtype != np.float64:
+        continue
     if variant == ac.CELL and os.environ.get("SKIP_CELL"):
         continue
     for step in range(3):

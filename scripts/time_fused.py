@@ -1,0 +1,59 @@
+"""Time the fused jacobi kernel variants on ONE GPU (same box, same run): the plain whole-region kernel as calibration,
+the fused schedule on one 512^3 subdomain, and -- as a single-GPU stand-in for the multi-rank kernels -- the same 512^3
+cut into 2 (x) and 8 (2x2x2) subdomains on this GPU, where every cut face is shipped (dense x arrays, ghost rows / planes)
+between subdomains exactly as between ranks, minus the flags and the NVLink latency.
+usage: python scripts/time_fused.py [n=512] [reps=30]"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import stencil_b200 as sb
+from stencil_b200.jacobi import Jacobi3D, jacobi_radius
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+dtype = np.float64 if os.environ.get("DTYPE", "f64") == "f64" else np.float32
+
+
+def run(ndom, label, fused=True):
+    dd = sb.DistributedDomain(n, n, n)
+    dd.set_gpus([0] * ndom)
+    dd.set_radius(jacobi_radius())
+    h = dd.add_data(dtype)
+    dd.realize()
+    jac = Jacobi3D(dd, h)
+    jac.init(0.5)
+    step = jac.step_fused if fused else jac.launch_whole
+    for _ in range(5):
+        step()
+    jac.synchronize()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    jac.synchronize()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    es = np.dtype(dtype).itemsize
+    print(f"{label:46s} {ms:.4f} ms/step  {2*es*n**3/ms/1e6:.0f} GB/s", flush=True)
+    jac.close()
+    dd.close()
+    return ms
+
+
+only = os.environ.get("ONLY")  # e.g. ONLY=2 -> just the 2-subdomain case with the default kernel (for ncu)
+if only:
+    run(int(only), f"fused (default variant) subdomains={only}")
+    sys.exit(0)
+run(1, "plain whole-region kernel (calibration)", fused=False)
+for nopush in ("", "1"):
+    if nopush:
+        os.environ["SB_DEBUG_NOPUSH"] = "1"  # timing only: nothing is shipped (results wrong)
+    for regs, split in (("64", "1"), ("64", "0"), ("56", "1")):
+        os.environ["SB_FUSED_REGS"], os.environ["SB_FUSED_SPLIT"] = regs, split
+        for ndom in (1, 2, 8):
+            run(ndom, f"fused regs={regs} split={split} subdomains={ndom}" + (" NOPUSH" if nopush else ""))

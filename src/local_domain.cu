@@ -21,18 +21,28 @@ LocalDomain::LocalDomain(Dim3 sz, Dim3 origin, int dev)
     : sz_(sz), origin_(origin), radius_(Radius::constant(0)), devCurrDataPtrs_(nullptr), devNextDataPtrs_(nullptr),
       devDataElemSize_(nullptr), dev_(dev) {}
 
+LocalDomain::LocalDomain(const LocalDomain &o)
+    : sz_(o.sz_), origin_(o.origin_), radius_(o.radius_), currDataPtrs_(o.currDataPtrs_), nextDataPtrs_(o.nextDataPtrs_),
+      dataElemSize_(o.dataElemSize_), dataName_(o.dataName_), devCurrDataPtrs_(nullptr), devNextDataPtrs_(nullptr), devDataElemSize_(nullptr),
+      dev_(o.dev_) {
+  if (!o.allocBases_.empty() || o.devCurrDataPtrs_) LOG_FATAL("LocalDomain copied after realize(): the copy would free the same device memory again");
+}
+
+LocalDomain::LocalDomain(LocalDomain &&o) noexcept
+    : sz_(o.sz_), origin_(o.origin_), radius_(o.radius_), currDataPtrs_(std::move(o.currDataPtrs_)), nextDataPtrs_(std::move(o.nextDataPtrs_)),
+      allocBases_(std::move(o.allocBases_)), dataElemSize_(std::move(o.dataElemSize_)), dataName_(std::move(o.dataName_)),
+      devCurrDataPtrs_(o.devCurrDataPtrs_), devNextDataPtrs_(o.devNextDataPtrs_), devDataElemSize_(o.devDataElemSize_), dev_(o.dev_) {
+  o.allocBases_.clear();
+  o.devCurrDataPtrs_ = o.devNextDataPtrs_ = nullptr;
+  o.devDataElemSize_ = nullptr;
+}
+
 LocalDomain::~LocalDomain() {
-  // NOTE: like the reference, copies of a LocalDomain share the raw device pointers; DistributedDomain
-  // only copies before realize() (while everything is still null), so exactly one object frees.
-  bool any = devCurrDataPtrs_ || devNextDataPtrs_ || devDataElemSize_;
-  for (const auto &p : currDataPtrs_) any = any || p.ptr;
-  for (const auto &p : nextDataPtrs_) any = any || p.ptr;
-  if (!any) return;
+  // frees exactly what realize() allocated (the block addresses recorded there: set_radius() after realize() must not
+  // change what is passed to cudaFree)
+  if (allocBases_.empty() && !devCurrDataPtrs_ && !devNextDataPtrs_ && !devDataElemSize_) return;
   CUDA_RUNTIME(cudaSetDevice(dev_));
-  for (size_t i = 0; i < currDataPtrs_.size(); ++i) {
-    if (currDataPtrs_[i].ptr) CUDA_RUNTIME(cudaFree(static_cast<char *>(currDataPtrs_[i].ptr) - lead_bytes(i)));
-    if (nextDataPtrs_[i].ptr) CUDA_RUNTIME(cudaFree(static_cast<char *>(nextDataPtrs_[i].ptr) - lead_bytes(i)));
-  }
+  for (void *b : allocBases_) CUDA_RUNTIME(cudaFree(b));
   if (devCurrDataPtrs_) CUDA_RUNTIME(cudaFree(devCurrDataPtrs_));
   if (devNextDataPtrs_) CUDA_RUNTIME(cudaFree(devNextDataPtrs_));
   if (devDataElemSize_) CUDA_RUNTIME(cudaFree(devDataElemSize_));
@@ -87,6 +97,7 @@ void LocalDomain::realize() {
       cudaPitchedPtr p{};
       CUDA_RUNTIME(cudaMalloc(&p.ptr, bytes + 32));
       CUDA_RUNTIME(cudaMemset(p.ptr, 0, bytes + 32));
+      allocBases_.push_back(p.ptr);
       p.ptr = static_cast<char *>(p.ptr) + lead_bytes(size_t(i));
       p.pitch = rowBytes; // unpitched on purpose, see the header
       p.xsize = rowBytes;

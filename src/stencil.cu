@@ -29,7 +29,7 @@ void set3(int64_t out[3], const Dim3 &d) {
 
 DistributedDomain::DistributedDomain(size_t x, size_t y, size_t z)
     : size_(x, y, z), placement_(nullptr), radius_(Radius::constant(0)), flags_(Method::Default),
-      strategy_(PlacementStrategy::NodeAware), parity_(0), mailbox_(nullptr), epoch_(0), numBytesCudaMpi_(0), numBytesColoDirectAccess_(0),
+      strategy_(PlacementStrategy::NodeAware), boundary_(Topology::Boundary::PERIODIC), parity_(0), mailbox_(nullptr), epoch_(0), numBytesCudaMpi_(0), numBytesColoDirectAccess_(0),
       numBytesColoPackMemcpyUnpack_(0), numBytesCudaMemcpyPeer_(0), numBytesCudaKernel_(0) {
 #ifdef STENCIL_SETUP_STATS
   timeMpiTopo_ = timeNodeGpus_ = timePeerEn_ = timePlacement_ = timePlan_ = timeRealize_ = timeCreate_ = 0;
@@ -129,7 +129,7 @@ void DistributedDomain::do_placement() {
     break;
   }
   nvtxRangePop();
-  topology_ = Topology(placement_->dim(), Topology::Boundary::PERIODIC);
+  topology_ = Topology(placement_->dim(), boundary_);
 }
 
 void DistributedDomain::realize() {
@@ -535,6 +535,25 @@ void DistributedDomain::plan_exchange() {
   }
   planFile.close();
   parity_ = 0;
+
+  // rank x rank payload bytes per exchange, for numpy.loadtxt (the reference dumps the same file: src/stencil.cu:476-503)
+  {
+    std::vector<double> mat(size_t(worldSize_) * size_t(worldSize_), 0.0);
+    for (size_t di = 0; di < domains_.size(); ++di)
+      for (const Msg &m : messages_from(domainIdx_[di])) {
+        double bytes = 0;
+        for (size_t q = 0; q < dataElemSize_.size(); ++q) bytes += double(dataElemSize_[q]) * double(m.ext.flatten());
+        mat[size_t(rank_) * size_t(worldSize_) + size_t(placement_->get_rank(m.dstIdx))] += bytes;
+      }
+    MPI_Allreduce(MPI_IN_PLACE, mat.data(), int(mat.size()), MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+    if (0 == rank_) {
+      std::ofstream matFile(outputPrefix_ + "mat_npy_loadtxt.txt");
+      for (int r = 0; r < worldSize_; ++r) {
+        for (int c = 0; c < worldSize_; ++c) matFile << mat[size_t(r) * size_t(worldSize_) + size_t(c)] << " ";
+        matFile << "\n";
+      }
+    }
+  }
 
   // every rank learns the global volume
   for (uint64_t *b : {&numBytesCudaMpi_, &numBytesColoDirectAccess_, &numBytesColoPackMemcpyUnpack_, &numBytesCudaMemcpyPeer_, &numBytesCudaKernel_})

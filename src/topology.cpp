@@ -10,8 +10,15 @@ Topology::OptionalNeighbor Topology::get_neighbor(const Dim3 &index, const Dim3 
     answer.index = (index + dir).wrap(grid_);
     answer.exists = true;
     break;
+  case Boundary::FIXED: {
+    // the grid ends at its faces: a step that leaves it has no neighbour
+    const Dim3 to = index + dir;
+    answer.exists = to.all_ge(0) && to.all_lt(grid_);
+    answer.index = answer.exists ? to : index;
+    break;
+  }
   default:
-    LOG_FATAL("Topology::get_neighbor: only periodic grids are supported");
+    LOG_FATAL("Topology::get_neighbor: the topology has no boundary kind (default-constructed?)");
   }
   return answer;
 }

@@ -50,7 +50,7 @@ class HaloPush(C.Structure):
     _fields_ = [("nbr", Pitched * 6), ("nbr_zsize", C.c_int64 * 6), ("x_dense", C.c_int64 * 2), ("x_recv", C.c_void_p * 2)]
 
 
-FUSED_MAX_GROUPS = 1024  # SB_FUSED_MAX_GROUPS
+FUSED_MAX_GROUPS = 4096  # SB_FUSED_MAX_GROUPS
 
 
 class StepSync(C.Structure):

@@ -18,7 +18,7 @@ from .domain import DataHandle, DistributedDomain
 
 FIELDS = ("lnrho", "uux", "uuy", "uuz", "ax", "ay", "az", "entropy")
 NGHOST = 3  # STENCIL_ORDER / 2, astaroth/astaroth.h:8-9
-AUTO, CELL, TILE, TEAM = 0, 1, 2, 3
+AUTO, CELL, TILE, TEAM, TEAM_TMA, TEAM3_TMA = 0, 1, 2, 3, 4, 5
 
 
 def conf_params(dt: float = 1e-8) -> AstarothParams:

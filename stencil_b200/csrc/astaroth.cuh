@@ -28,7 +28,10 @@ enum AcVariant {
   AC_AUTO = 0,   // tile kernel for thick regions, cell kernel for thin ones
   AC_CELL = 1,   // one thread per cell, neighbours through L1/L2
   AC_TILE = 2,   // z-march over a shared-memory ring of halo'd planes (cp.async pipeline), one thread per cell
-  AC_TEAM = 3,   // the same ring, two specialised threads per cell (velocity/thermodynamics team + induction team)
+  AC_TEAM = 3,   // the same ring, two specialised threads per cell (velocity/thermodynamics team + induction team);
+                 // FP64: the ring is fed by TMA (one bulk tensor copy per field and plane) when the buffers allow it
+  AC_TEAM_TMA = 4,  // the TMA-fed two-team kernel or an error (tests)
+  AC_TEAM3_TMA = 5, // the TMA-fed three-team kernel (thermodynamics / velocity / induction) or an error
 };
 
 // solve<step> on the box [lo, hi) in memory-offset coordinates (the reference's IDX(i,j,k) = i + j*mx + k*mx*my);

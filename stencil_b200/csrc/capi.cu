@@ -828,6 +828,7 @@ int sb_jacobi3d_fused_sync(sb_pitched dst, sb_pitched src, int dtype_size, const
   auto self = [&](int d) { return push->nbr[d].ptr == dst.ptr && push->nbr[d].pitch == dst.pitch && push->nbr[d].ysize == dst.ysize; };
   if (self(0) && self(1)) p.xwrap = 1; // a request: launch_jacobi_fused keeps the x pushes when the vector layout rules it out
   if (self(2) && self(3) && (src.pitch % 16 == 0 || (p.hi[1] - p.lo[1]) % 2 == 0)) p.ywrap = 1, p.push_ptr[2] = p.push_ptr[3] = nullptr;
+  if (self(4) && self(5)) p.zwrap = 1, p.push_ptr[4] = p.push_ptr[5] = nullptr; // planes have one phase: nothing else to check
   const int n = sb::launch_jacobi_fused(p, fs, dtype_size, static_cast<cudaStream_t>(stream));
   if (n == -1) return fail(SB_ERR_INVALID, "a dense received x array needs a 16-byte aligned first compute cell and whole warp strips along x");
   if (n == -2) return fail(SB_ERR_INVALID, "more than %d z chunks or tile rows: too tall for the fused kernel's face groups", SB_FUSED_MAX_GROUPS);
@@ -842,7 +843,7 @@ int sb_astaroth_substep(int step, const void *const in[8], void *const out[8], i
   if (!in || !out || !raw || !lo || !hi || !params) return fail(SB_ERR_INVALID, "null argument");
   if (step < 0 || step > 2) return fail(SB_ERR_INVALID, "substep %d (Williamson RK3 has substeps 0, 1, 2)", step);
   if (dtype_size != 4 && dtype_size != 8) return fail(SB_ERR_INVALID, "dtype_size %d (4 = float, 8 = double)", dtype_size);
-  if (variant < 0 || variant > 3) return fail(SB_ERR_INVALID, "variant %d", variant);
+  if (variant < 0 || variant > 5) return fail(SB_ERR_INVALID, "variant %d", variant);
   sb::AcFields f;
   for (int i = 0; i < sb::kAcFields; ++i) {
     if (!in[i] || !out[i]) return fail(SB_ERR_INVALID, "field %d is null", i);

@@ -78,7 +78,7 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // instead of the ghost column (EDGE = 3).  Nothing is pushed inside the loop: the faces are shipped afterwards by the
 // last CTA of each face group (jacobi_fused_kernel).
 template <typename T, int VX, int RY, bool SHIFT, int PUSH> // PUSH (= EDGE): 0 plain, 2 boundary CTA, 3 boundary CTA with dense x ghosts
-__device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, const int by, const int bz) {
+__device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, const int by, const int bz, const bool wait_barrier = false) {
   static_assert(!SHIFT || (RY == 1 && VX >= 2), "the phase-shifted variant handles one row per warp");
   static_assert(!PUSH || RY == 1, "the push variant handles one row per warp");
   using V = Vec<T, VX>;
@@ -94,7 +94,10 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   const int x = x0w + lane * VX;                              // first cell of this lane
   const int z0 = p.lo[2] + bz * p.zchunk;
   const int z1 = min(z0 + p.zchunk, p.hi[2]);
-  if (y >= p.hi[1] || x0w >= p.hi[0]) return; // warp-uniform
+  if (y >= p.hi[1] || x0w >= p.hi[0]) { // warp-uniform
+    if (wait_barrier) __syncthreads();
+    return;
+  }
 
   // does this lane's vector lie inside the allocation row?  (SHIFT: a vector may hang over either end
   // of its row into the neighbouring row of the same allocation -- valid memory, masked cells)
@@ -157,11 +160,54 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   }
   const int gx0 = x + p.org[0];
 
+  // ---- EDGE: what this warp contributes to the neighbours' halos (see jacobi_fused_kernel).  No global load is ever
+  // issued for it after the march: under a saturated memory system a dependent load costs microseconds.
+  //  x faces: the lane holding the first / last cell of the row parks it in shared memory every step (one predicated STS);
+  //           after the march the warp writes the row's chunk with one store per lane (a 256-byte line of the dense array).
+  //  y faces: the warp that owns the first / last row stores its vector a second time, into the neighbour's ghost row,
+  //           through a loop-invariant address difference (one predicated vector store per step).
+  //  z faces: the last plane of the chunk is still in registers after the loop; the first one is re-read (own store).
+  __shared__ T xstage[PUSH ? 2 : 1][PUSH ? 8 : 1][PUSH ? 32 : 1];
+  int xsi = -1;       // which element of this lane's vector is an x-face cell (-1: none; a lane never holds both faces: ex >= 16)
+  T *xsp = nullptr;   // where that cell of the current plane is parked
+  long long ydiff = 0;
+  bool ypush = false, ypost = false;
+  int ydir = -1;
+  if (PUSH && row_ok[0]) {
+#pragma unroll
+    for (int i = 0; i < VX; ++i) {
+      if (x + i == p.lo[0] && p.push_ptr[0]) xsi = i, xsp = &xstage[0][warp][0];
+      if (x + i == p.hi[0] - 1 && p.push_ptr[1]) xsi = i, xsp = &xstage[1][warp][0];
+    }
+    ydir = (y == p.lo[1] && p.push_ptr[2]) ? 2 : ((y == p.hi[1] - 1 && p.push_ptr[3]) ? 3 : -1);
+    if (ydir >= 0) {
+      ydiff = (p.push_ptr[ydir] + (long long)x * (long long)sizeof(T) + (long long)z0 * S) - pw[0];
+      // in the loop only if every lane can store its whole vector, aligned, and the neighbour's planes are as far apart as
+      // ours; anything else (odd sizes, phase-shifted FP32 rows) is copied after the march from this warp's own stores
+      const bool ok = p.push_slice[ydir] == S && ((unsigned long long)(pw[0] + ydiff) % sizeof(V)) == 0 && (full || !cell_ok);
+      ypush = __all_sync(0xffffffffu, ok);
+      ypost = !ypush;
+    }
+  }
+  // a one-row subdomain faces both y neighbours: the second side goes the slow way
+  const bool ypost_hi = PUSH && row_ok[0] && ydir == 2 && y == p.hi[1] - 1 && p.push_ptr[3];
+
+  // boundary CTAs of the fused kernel: the flag poll issued before all this set-up must have completed before any load
+  if (wait_barrier) __syncthreads();
   V A[RY], B[RY], C[RY];
 #pragma unroll
   for (int j = 0; j < RY; ++j) {
-    A[j] = *reinterpret_cast<const V *>(pc[j] - 2 * S); // plane z0-1
-    B[j] = *reinterpret_cast<const V *>(pc[j] - S);     // plane z0
+    // plane z0-1 (a periodic self-neighbour along z: the ghost plane below the subdomain is its own top plane, read in place)
+    const char *pa = pc[j] - 2 * S;
+    if (PUSH && p.zwrap && z0 == p.lo[2]) pa += (long long)(p.hi[2] - p.lo[2]) * S;
+    A[j] = *reinterpret_cast<const V *>(pa);
+    B[j] = *reinterpret_cast<const V *>(pc[j] - S); // plane z0
+  }
+  // ... and the plane above the top one is the bottom plane: pc jumps down before the last step of the top chunk
+  const int zjump = (PUSH && p.zwrap && z1 == p.hi[2]) ? p.hi[2] - 1 : -1;
+  if (PUSH && zjump == z0) {
+#pragma unroll
+    for (int j = 0; j < RY; ++j) pc[j] -= (long long)(p.hi[2] - p.lo[2]) * S;
   }
   const int zlast = p.raw[2] - 1; // last plane that may be touched (prefetch guard)
   int z = z0;
@@ -230,6 +276,16 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
             if (cell_ok & (1u << i)) reinterpret_cast<T *>(pw[j])[i] = out.v[i];
         }
       }
+      if (PUSH) {
+        if (xsi >= 0) {
+          T v = out.v[0];
+#pragma unroll
+          for (int i = 1; i < VX; ++i)
+            if (xsi == i) v = out.v[i];
+          *xsp++ = v;
+        }
+        if (ypush && full) *reinterpret_cast<V *>(pw[j] + ydiff) = out;
+      }
       pc[j] += S;
       ph[j] += (PUSH == 3) ? phstep : S;
       pw[j] += S;
@@ -237,6 +293,10 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
     pu += S;
     pd += S;
     ++z;
+    if (PUSH && z == zjump) {
+#pragma unroll
+      for (int j = 0; j < RY; ++j) pc[j] -= (long long)(p.hi[2] - p.lo[2]) * S;
+    }
   };
 
   while (z < z1) {
@@ -247,6 +307,58 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
     step(C, A, B);
   }
 
+  if (PUSH) {
+    const long long es = (long long)sizeof(T);
+    const int np = z1 - z0;
+    // x faces: the staged column of this row, one plane per lane
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const bool mine = xsi >= 0 && (side == 0 ? x + xsi == p.lo[0] : x + xsi == p.hi[0] - 1);
+      if (!__ballot_sync(0xffffffffu, mine)) continue; // warp-uniform
+      __syncwarp();
+      if (lane < np) {
+        char *t = p.xdense[side] ? p.push_ptr[side] + (long long)y * p.push_pitch[side] + (long long)(z0 + lane) * es
+                                 : p.push_ptr[side] + (long long)(z0 + lane) * p.push_slice[side] + (long long)y * p.push_pitch[side];
+        *reinterpret_cast<T *>(t) = xstage[side][warp][lane];
+      }
+    }
+    // z faces: this lane's own stores of the first / last plane of the chunk, read back (one load per lane; the z-face CTAs
+    // are 1 in 8 and, with the rotated z order, not the last ones of the grid)
+    if (row_ok[0] && cell_ok) {
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        if (!(side == 0 ? z0 == p.lo[2] : z1 == p.hi[2]) || !p.push_ptr[4 + side]) continue;
+        const int zf = side == 0 ? z0 : z1 - 1;
+        const char *r = p.dst + (long long)zf * S + (long long)y * P + (long long)x * es;
+        char *t = p.push_ptr[4 + side] + (long long)y * p.push_pitch[4 + side] + (long long)x * es;
+        if (full && ((unsigned long long)t % sizeof(V)) == 0) {
+          V v;
+#pragma unroll
+          for (int i = 0; i < VX; ++i) v.v[i] = __ldcg(reinterpret_cast<const T *>(r) + i);
+          *reinterpret_cast<V *>(t) = v;
+        } else {
+#pragma unroll
+          for (int i = 0; i < VX; ++i)
+            if (cell_ok & (1u << i)) reinterpret_cast<T *>(t)[i] = __ldcg(reinterpret_cast<const T *>(r) + i);
+        }
+      }
+    }
+    // y faces the loop could not serve: copied from this lane's own stores, plane by plane
+    if (ypost || ypost_hi) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int d = k == 0 ? ydir : 3;
+        if (k == 0 ? !ypost : !ypost_hi) continue;
+        const char *r = p.dst + (long long)y * P + (long long)x * es;
+        char *t = p.push_ptr[d] + (long long)x * es;
+        for (int zz = z0; zz < z1; ++zz) {
+#pragma unroll
+          for (int i = 0; i < VX; ++i)
+            if (cell_ok & (1u << i)) reinterpret_cast<T *>(t + (long long)zz * p.push_slice[d])[i] = __ldcg(reinterpret_cast<const T *>(r + (long long)zz * S) + i);
+        }
+      }
+    }
+  }
 }
 
 template <typename T, int VX, int RY, int MB, bool SHIFT>
@@ -264,105 +376,45 @@ __global__ void __launch_bounds__(256, MB) jacobi_march_kernel(const __grid_cons
 //  * Blocks run in the natural order (x fastest): measured, gathering the boundary CTAs at the start or the end of the
 //    grid costs 10 % (their 512-byte row segments lose the DRAM locality of whole rows).  CTAs that touch no face of the
 //    subdomain (64 % at 512^3) run the plain loop; boundary CTAs run the EDGE variant, which differs only in where the
-//    cells just outside the subdomain come from.  No push code inside any loop (it cost 36 % more issued instructions).
-//  * Face groups.  The cells of face f computed by one group of boundary CTAs form a slab of ~2048 cells that is shipped
-//    in one piece (struct Groups below): x faces -- 64 rows x zchunk planes of the column, y faces -- one strip of the row x
-//    zchunk planes, z faces -- 8 rows of the plane.  Every boundary CTA counts itself into the
-//    groups it belongs to (release at GPU scope); the LAST one to arrive re-reads the slab from dst (L2) and stores it
-//    into the neighbour -- ghost rows / planes, the ghost column, or the neighbour's dense x array -- then, if the
-//    neighbour is another rank, fences at system scope and publishes the iteration number in the neighbour's mailbox word
-//    for that group (st.release.sys).  ~220 of 8192 CTAs ship; only they pay an NVLink round trip.
-//  * Waiting.  Before marching, a boundary CTA polls the mailbox words of ITS groups (ld.acquire.sys, own memory) until
-//    the neighbour has shipped the previous iteration's slab: that one flag says both "the ghost cells I read are
-//    filled" and "the neighbour's group is done reading the ghost cells my group's shipper will overwrite".  Neighbours
-//    walk their grids in the same order, so the word a CTA needs was written a whole iteration earlier: x / y groups
-//    by construction, z groups because the z order is rotated by half the chunks (s.zrot) -- without the rotation the
-//    first chunk of iteration e+1 would need what the last chunk of iteration e ships.
+//    cells just outside the subdomain come from.  No push code inside any loop (measured: it cost 36 % more issued
+//    instructions in every boundary CTA).
+//  * Pushing.  A boundary CTA stores its own face cells into the neighbour as it marches (march_body, EDGE): x cells are
+//    parked in shared memory and leave as one 256-byte line per row and chunk, y rows are stored a second time by the warp
+//    that owns them, the +z plane goes out from the registers of the last step.  Nothing is counted, nothing crosses CTAs,
+//    and no global load follows the march (tried: a copy pass over the finished tile costs microseconds per CTA under a
+//    saturated memory system, and re-reading through a "last CTA of a group" costs an L1 invalidation per fence).
+//  * Signalling.  If the neighbour is another rank, warp 0 -- the other warps exit after arriving at a named barrier --
+//    fences at system scope and publishes the iteration number in the neighbour's mailbox word for this tile
+//    (st.release.sys).  A CTA's registers return to the SM only when its last warp exits, and at 64 registers a new CTA
+//    needs all of them (4 x 256 x 64 = the whole file): the 56-register build lets a new CTA start beside four such
+//    stragglers.
+//  * Waiting.  Before its first load a boundary CTA polls the mailbox words of the tiles across its faces (own memory)
+//    until the neighbour has shipped the previous iteration: that one flag says both "the ghost cells I read are filled"
+//    and "the neighbour's tile is done reading the ghost cells I am about to overwrite".  Neighbours walk their grids in
+//    the same order, so the word was written a whole iteration earlier: x / y tiles by construction, z tiles because the
+//    z order is rotated by half the chunks (s.zrot) -- without the rotation the first chunk of iteration e+1 would need
+//    what the last chunk of iteration e ships.  ONE thread polls with relaxed loads and fences once: every acquire
+//    (ld.acquire, fence.acq_rel) also invalidates the SM's whole L1 (CCTL.IVALL), which stalls the co-resident CTAs.
 constexpr int kMaxGroups = SB_FUSED_MAX_GROUPS;
 
-// Group geometry (the same on both sides of a face: neighbours across a face have equal extents on the other two axes).
-// Slabs are kept to ~2048 cells so that the CTA that ships one reads it in one or two batches of independent loads:
-//   x face: group (z chunk, 8 tile rows)  = 64 rows x zchunk planes of the column,  members: the 8 (x nxhi) CTAs of those rows
-//   y face: group (z chunk, x tile)       = zchunk planes x one strip of the row,    members: 1
-//           (phase-shifted rows, SHIFT: strips of neighbouring rows do not line up -> one group per z chunk, members nx)
-//   z face: group (tile row)              = 8 rows x all x of the plane,             members: the nx CTAs of that tile row
-struct Groups {
-  int ny8; // x-face groups per z chunk
-  int nx;  // y-face groups per z chunk
-};
-template <bool SHIFT> __device__ __forceinline__ int group_of(int f, int bx, int by, int bz, const Groups &g) {
-  return f < 2 ? bz * g.ny8 + (by >> 3) : (f < 4 ? (SHIFT ? bz : bz * g.nx + bx) : by);
+// mailbox word of the tile (bx, by, bz) on face f: the same arithmetic on both sides of the face (neighbours across a
+// face have equal extents on the other two axes, hence equal tile counts there)
+__device__ __forceinline__ int tile_slot(int f, int bx, int by, int bz, int nx, int ny) {
+  return f < 2 ? bz * ny + by : (f < 4 ? bz * nx + bx : by * nx + bx);
 }
 
-// all 256 threads: copy `total` cells; cell i is read from src_of(i) and stored to dst_of(i).  Eight independent loads per
-// thread are in flight before the first store (a shipper is the tail of its group: latency, not bandwidth, is what counts)
-template <typename T, typename SrcOf, typename DstOf> __device__ __forceinline__ void ship_cells(int total, SrcOf src_of, DstOf dst_of) {
-  for (int base = threadIdx.x; base < total; base += 256 * 8) {
-    T v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = base + k * 256;
-      if (i < total) v[k] = __ldcg(reinterpret_cast<const T *>(src_of(i)));
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = base + k * 256;
-      if (i < total) *reinterpret_cast<T *>(dst_of(i)) = v[k];
-    }
-  }
-}
+template <typename T, int VX, bool SHIFT> __device__ __noinline__ void signal_tile(const JacobiParams &p, const FusedSync &s, int nx, int ny, int nz);
 
-// copy the slab of face f that belongs to the group of tile (bx, by, bz) from dst into the neighbour
-template <typename T, int VX, bool SHIFT> __device__ __forceinline__ void ship_face(const JacobiParams &p, int f, int bx, int by, int bz) {
-  const long long S = p.slice, P = p.pitch;
-  const long long es = (long long)sizeof(T);
-  const int z0 = p.lo[2] + bz * p.zchunk, z1 = min(z0 + p.zchunk, p.hi[2]);
-  if (f < 2) { // x face: column xc, the 64 rows of 8 tile rows, planes [z0, z1); consecutive threads along z (dense target: z fastest)
-    const int xc = f == 0 ? p.lo[0] : p.hi[0] - 1;
-    const int np = z1 - z0;
-    const int y0 = p.lo[1] + (by >> 3) * 64, rows = min(64, p.hi[1] - y0);
-    const char *src = p.dst + (long long)xc * es;
-    char *tgt = p.push_ptr[f];
-    const long long tp = p.push_pitch[f], ts = p.xdense[f] ? es : p.push_slice[f];
-    ship_cells<T>(
-        rows * np, [&](int i) { return src + (long long)(z0 + i % np) * S + (long long)(y0 + i / np) * P; },
-        [&](int i) { return tgt + (long long)(y0 + i / np) * tp + (long long)(z0 + i % np) * ts; });
-  } else if (f < 4) { // y face: row yf, planes [z0, z1), the cells of this x strip (SHIFT: the whole row)
-    const int yf = f == 2 ? p.lo[1] : p.hi[1] - 1;
-    const int xa = SHIFT ? p.lo[0] : max(p.lo[0], p.x0a + bx * 32 * VX), xb = SHIFT ? p.hi[0] : min(p.hi[0], p.x0a + (bx + 1) * 32 * VX);
-    const int ex = xb - xa;
-    if (ex <= 0) return;
-    const char *src = p.dst + (long long)yf * P + (long long)xa * es;
-    char *tgt = p.push_ptr[f] + (long long)xa * es;
-    const long long ts = p.push_slice[f];
-    ship_cells<T>(
-        ex * (z1 - z0), [&](int i) { return src + (long long)(z0 + i / ex) * S + (long long)(i % ex) * es; },
-        [&](int i) { return tgt + (long long)(z0 + i / ex) * ts + (long long)(i % ex) * es; });
-  } else { // z face: plane zf, the 8 rows of tile row `by`, all x
-    const int zf = f == 4 ? p.lo[2] : p.hi[2] - 1;
-    const int ex = p.hi[0] - p.lo[0];
-    const int y0 = p.lo[1] + by * 8, rows = min(8, p.hi[1] - y0);
-    const char *src = p.dst + (long long)zf * S + (long long)p.lo[0] * es;
-    char *tgt = p.push_ptr[f] + (long long)p.lo[0] * es;
-    const long long tp = p.push_pitch[f];
-    ship_cells<T>(
-        ex * rows, [&](int i) { return src + (long long)(y0 + i / ex) * P + (long long)(i % ex) * es; },
-        [&](int i) { return tgt + (long long)(y0 + i / ex) * tp + (long long)(i % ex) * es; });
-  }
-}
-
-template <typename T, int VX, bool SHIFT, int EDGE>
-__global__ void __launch_bounds__(256, 4)
-    jacobi_fused_kernel(const __grid_constant__ JacobiParams p, const __grid_constant__ FusedSync s, int nx, int ny, int nz) {
+template <typename T, int VX, bool SHIFT, int EDGE, bool SPLIT>
+__device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSync &s, int nx, int ny, int nz) {
   int b = blockIdx.x;
   const int bx = b % nx;
   b /= nx;
   const int by = b % ny;
   int bz = b / ny + s.zrot;
   if (bz >= nz) bz -= nz;
-  const Groups g{(ny + 7) >> 3, nx};
   // the faces this CTA's cells lie on (phase-shifted rows end one strip later than the others, so with SHIFT the last TWO
-  // strips along x may hold cells of the +x face); only faces with something to push form groups
+  // strips along x may hold cells of the +x face)
   const int nxhi = SHIFT ? min(nx, 2) : 1;
   unsigned touch = 0;
   if (bx == 0) touch |= 1u;
@@ -371,7 +423,7 @@ __global__ void __launch_bounds__(256, 4)
   if (by == ny - 1) touch |= 8u;
   if (bz == 0) touch |= 16u;
   if (bz == nz - 1) touch |= 32u;
-  if (!touch) {
+  if (SPLIT && !touch) { // CTAs that touch no face take the plain loop (a second copy of the loop in the kernel)
     march_body<T, VX, 1, SHIFT, 0>(p, bx, by, bz);
     return;
   }
@@ -380,63 +432,86 @@ __global__ void __launch_bounds__(256, 4)
   for (int f = 0; f < 6; ++f)
     if ((touch >> f & 1u) && p.push_ptr[f]) faces |= 1u << f;
 
-  if (s.any_wait && faces) {
-    const int f = threadIdx.x;
-    if (f < 6 && (faces >> f & 1u) && s.wait_row[f]) {
-      const uint32_t want = s.wait_value;
-      const uint32_t *slot = s.wait_row[f] + group_of<SHIFT>(f, bx, by, bz, g);
+  // poll first, synchronise late: the barrier that publishes the poll to the other warps sits inside march_body, after its
+  // address set-up and right before its first load
+  const bool waits = s.any_wait && faces;
+  if (waits && threadIdx.x == 0) {
+    const uint32_t want = s.wait_value;
+    auto poll = [&](const uint32_t *slot) {
       uint32_t v;
       while (true) {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
         if ((int32_t)(v - want) >= 0) break; // wrap-safe "v >= want"
         __nanosleep(100);
       }
-    }
-    __syncthreads();
-  }
-
-  march_body<T, VX, 1, SHIFT, EDGE>(p, bx, by, bz);
-  if (!faces) return;
-
-  __shared__ unsigned last_mask;
-  __syncthreads(); // every thread's stores to dst are issued ...
-  if (threadIdx.x == 0) {
-    __threadfence(); // ... and visible GPU-wide before this CTA counts itself in
-    unsigned m = 0;
+    };
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
-      if (!(faces >> f & 1u)) continue;
-      // x: the tile rows of this group (the last group may be short) x the strips holding the face; y: one strip; z: all strips
-      const unsigned members = f < 2 ? unsigned(min(8, ny - (by & ~7))) * (f == 1 ? unsigned(nxhi) : 1u) : (f < 4 && !SHIFT ? 1u : unsigned(nx));
-      uint32_t *cnt = s.counters + f * kMaxGroups + group_of<SHIFT>(f, bx, by, bz, g);
-      if (atomicAdd(cnt, 1u) == members - 1u) {
-        *cnt = 0; // the next launch on this stream starts from zero
-        m |= 1u << f;
+      if (!(faces >> f & 1u) || !s.wait_row[f]) continue;
+      poll(s.wait_row[f] + tile_slot(f, bx, by, bz, nx, ny));
+      if (SHIFT && (f == 2 || f == 3)) { // strips of rows of different phase overlap their neighbours by VX / 2 cells
+        if (bx > 0) poll(s.wait_row[f] + tile_slot(f, bx - 1, by, bz, nx, ny));
+        if (bx + 1 < nx) poll(s.wait_row[f] + tile_slot(f, bx + 1, by, bz, nx, ny));
       }
     }
-    if (m) __threadfence(); // acquire: the other members' stores
-    last_mask = m;
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
   }
-  __syncthreads();
-  const unsigned mine = last_mask;
-  if (!mine) return;
-#pragma unroll
-  for (int f = 0; f < 6; ++f)
-    if (mine >> f & 1u) ship_face<T, VX, SHIFT>(p, f, bx, by, bz);
-  bool signal = false;
-#pragma unroll
-  for (int f = 0; f < 6; ++f)
-    if ((mine >> f & 1u) && s.signal_row[f]) signal = true;
-  if (!signal) return; // neighbours inside this process are ordered by stream events
-  __syncthreads();     // all of the slab is on its way ...
+
+  march_body<T, VX, 1, SHIFT, EDGE>(p, bx, by, bz, waits); // pushes this tile's face cells as it goes
+  if (s.any_signal) signal_tile<T, VX, SHIFT>(p, s, nx, ny, nz);
+}
+
+// After the march of a boundary CTA whose neighbour is another rank: publish the iteration number in the neighbour's mailbox
+// word for this tile.  Everything is derived again from the block index (read through an opaque asm, so that the
+// compiler does not keep tile coordinates and face masks alive across the marching loop).  Only warp 0 stays: the others
+// arrive at a named barrier and exit -- a CTA's registers return to the SM when its LAST warp exits, and the fence below
+// waits for an NVLink round trip.
+template <typename T, int VX, bool SHIFT> __device__ __noinline__ void signal_tile(const JacobiParams &p, const FusedSync &s, int nx, int ny, int nz) {
+  int b;
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(b));
+  const int bx = b % nx;
+  b /= nx;
+  const int by = b % ny;
+  int bz = b / ny + s.zrot;
+  if (bz >= nz) bz -= nz;
+  const int nxhi = SHIFT ? min(nx, 2) : 1;
+  unsigned faces = 0;
+  if (bx == 0 && p.push_ptr[0] && s.signal_row[0]) faces |= 1u;
+  if (bx >= nx - nxhi && p.push_ptr[1] && s.signal_row[1]) faces |= 2u;
+  if (by == 0 && p.push_ptr[2] && s.signal_row[2]) faces |= 4u;
+  if (by == ny - 1 && p.push_ptr[3] && s.signal_row[3]) faces |= 8u;
+  if (bz == 0 && p.push_ptr[4] && s.signal_row[4]) faces |= 16u;
+  if (bz == nz - 1 && p.push_ptr[5] && s.signal_row[5]) faces |= 32u;
+  if (!faces) return; // CTA-uniform
+  if (threadIdx.x >= 32) {
+    asm volatile("bar.arrive 1, 256;" ::: "memory"); // my pushes are issued (ordered before warp 0's fence at CTA scope)
+    return;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   if (threadIdx.x == 0) {
-    __threadfence_system(); // ... and has landed in the neighbour before the flag does
+    __threadfence_system(); // every warp's pushes have landed in the neighbour before the flag does
     const uint32_t value = s.signal_value;
 #pragma unroll
     for (int f = 0; f < 6; ++f)
-      if ((mine >> f & 1u) && s.signal_row[f])
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.signal_row[f] + group_of<SHIFT>(f, bx, by, bz, g)), "r"(value) : "memory");
+      if (faces >> f & 1u)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.signal_row[f] + tile_slot(f, bx, by, bz, nx, ny)), "r"(value) : "memory");
   }
+}
+
+// Variants (SB_FUSED_REGS, SB_FUSED_SPLIT; defaults chosen by measurement, profiles/README.md):
+//   REGS 64 / 56: with 64 registers a CTA's last warp -- lingering in the fences of the arrival / shipping code after the
+//     other seven have exited -- holds registers the next CTA needs (4 x 256 x 64 = the whole file); with 56 a new CTA fits
+//     next to four stragglers, at the price of a spilled loop invariant.
+//   SPLIT: CTAs that touch no face run a second, plain copy of the loop.
+template <typename T, int VX, bool SHIFT, int EDGE, bool SPLIT>
+__global__ void __maxnreg__(56)
+    jacobi_fused_kernel56(const __grid_constant__ JacobiParams p, const __grid_constant__ FusedSync s, int nx, int ny, int nz) {
+  fused_body<T, VX, SHIFT, EDGE, SPLIT>(p, s, nx, ny, nz);
+}
+template <typename T, int VX, bool SHIFT, int EDGE, bool SPLIT>
+__global__ void __launch_bounds__(256, 4)
+    jacobi_fused_kernel(const __grid_constant__ JacobiParams p, const __grid_constant__ FusedSync s, int nx, int ny, int nz) {
+  fused_body<T, VX, SHIFT, EDGE, SPLIT>(p, s, nx, ny, nz);
 }
 
 // One thread per cell: thin regions (the +-x exterior slabs are 1..r cells wide in x).
@@ -572,17 +647,26 @@ template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p
   const int ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
   const int tiles_z = (nz + p.zchunk - 1) / p.zchunk;
   const int tiles_y = (ny + 7) / 8;
-  if ((long long)tiles_z * ((tiles_y + 7) / 8) > kMaxGroups || (long long)tiles_z * tiles_x > kMaxGroups || tiles_y > kMaxGroups) return -2;
+  if ((long long)tiles_z * tiles_y > kMaxGroups || (long long)tiles_z * tiles_x > kMaxGroups || (long long)tiles_y * tiles_x > kMaxGroups) return -2;
   const long long blocks = (long long)tiles_x * tiles_y * tiles_z;
   // start in the middle of z when a z face waits for another rank (see the kernel's header)
   s.zrot = (s.wait_row[4] || s.wait_row[5]) ? tiles_z / 2 : 0;
-  s.any_wait = 0;
-  for (int f = 0; f < 6; ++f)
+  s.any_wait = s.any_signal = 0;
+  for (int f = 0; f < 6; ++f) {
     if (s.wait_row[f]) s.any_wait = 1;
-  if (p.xghost_ptr[0] || p.xghost_ptr[1])
-    jacobi_fused_kernel<T, VX, SHIFT, 3><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
-  else
-    jacobi_fused_kernel<T, VX, SHIFT, 2><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
+    if (s.signal_row[f]) s.any_signal = 1;
+  }
+  const bool regs56 = env_int("SB_FUSED_REGS", 56) == 56;
+  const bool split = env_int("SB_FUSED_SPLIT", 1) != 0;
+  const bool dense_ghosts = p.xghost_ptr[0] || p.xghost_ptr[1];
+  auto go = [&](auto kern) { kern<<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z); };
+  if (regs56) {
+    if (dense_ghosts) split ? go(jacobi_fused_kernel56<T, VX, SHIFT, 3, true>) : go(jacobi_fused_kernel56<T, VX, SHIFT, 3, false>);
+    else split ? go(jacobi_fused_kernel56<T, VX, SHIFT, 2, true>) : go(jacobi_fused_kernel56<T, VX, SHIFT, 2, false>);
+  } else {
+    if (dense_ghosts) split ? go(jacobi_fused_kernel<T, VX, SHIFT, 3, true>) : go(jacobi_fused_kernel<T, VX, SHIFT, 3, false>);
+    else split ? go(jacobi_fused_kernel<T, VX, SHIFT, 2, true>) : go(jacobi_fused_kernel<T, VX, SHIFT, 2, false>);
+  }
   return 1;
 }
 
@@ -722,22 +806,6 @@ static int pick_vectors(JacobiParams &p, int dtype_size, bool allow_shift, bool 
   return origin(1, 0);
 }
 
-// Arrival counters of the face groups: one zeroed block per (device, stream).  Launches on one stream are serialised and
-// every group's last arrival resets its counter, so the block is all zero again whenever the next launch starts.
-static uint32_t *group_counters(cudaStream_t stream) {
-  static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, uint32_t *> pool;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> lk(mu);
-  uint32_t *&c = pool[std::make_pair(dev, stream)];
-  if (!c) {
-    if (cudaMalloc(&c, 6 * kMaxGroups * sizeof(uint32_t)) != cudaSuccess) return nullptr;
-    cudaMemsetAsync(c, 0, 6 * kMaxGroups * sizeof(uint32_t), stream);
-  }
-  return c;
-}
-
 int launch_jacobi_fused(const JacobiParams &p_in, const FusedSync &sync_in, int dtype_size, cudaStream_t stream) {
   JacobiParams p = p_in;
   const int ex = p.hi[0] - p.lo[0], ey = p.hi[1] - p.lo[1], ez = p.hi[2] - p.lo[2];
@@ -745,12 +813,15 @@ int launch_jacobi_fused(const JacobiParams &p_in, const FusedSync &sync_in, int 
   static const int zchunk_env = env_int("SB_JACOBI_ZCHUNK", 0);
   static const int pf = env_int("SB_JACOBI_PREFETCH", 2);
   static const int allow_shift = env_int("SB_JACOBI_SHIFT", 1);
-  p.zchunk = zchunk_env > 0 ? zchunk_env : 32;
+  p.zchunk = (zchunk_env > 0 && zchunk_env <= 32) ? zchunk_env : 32; // the x faces are staged 32 planes at a time
   if (p.zchunk > ez) p.zchunk = ez;
   p.prefetch = pf;
   FusedSync sync = sync_in;
-  if (!sync.counters) sync.counters = group_counters(stream);
-  if (!sync.counters) return -3;
+  const int dbg = env_int("SB_DEBUG_FUSED", 0); // timing diagnostics only (results may be wrong): 1 no waits, 2 no signals
+  for (int f = 0; f < 6; ++f) {
+    if (dbg & 1) sync.wait_row[f] = nullptr;
+    if (dbg & 2) sync.signal_row[f] = nullptr;
+  }
   bool shift = false;
   const int vx = pick_vectors(p, dtype_size, allow_shift != 0, &shift);
   // x wrap (periodic self-neighbour read in place) works through the edge lanes' scalar load, so the first compute cell

@@ -30,10 +30,10 @@ struct JacobiParams {
   char *push_ptr[6];
   long long push_pitch[6];
   long long push_slice[6];
-  // periodic self-neighbour along x / y (fused launch only): the first / last column (row) takes its out-of-subdomain
+  // periodic self-neighbour along x / y / z (fused launch only): the first / last column (row) takes its out-of-subdomain
   // neighbour from the OPPOSITE face of src instead of from the ghost cells -- a pointer set up before the marching loop,
   // so that axis needs no exchange and no push at all
-  int xwrap, ywrap;
+  int xwrap, ywrap, zwrap;
   // dense x faces between ranks (fused launch, mode 3): xdense[d] != 0 means push_ptr[d] is not a ghost column but a
   // dense array [y][z] (z fastest, this subdomain's allocation coordinates; push_pitch[d] = bytes per row) in the
   // NEIGHBOUR's memory: the column is staged in shared memory and written out as one 256-byte line per row and chunk
@@ -44,18 +44,18 @@ struct JacobiParams {
   long long xghost_pitch[2];
 };
 
-// Face groups of the fused kernel (see jacobi_fused_kernel): at most this many z chunks / tile rows per subdomain
+// Mailbox rows of the fused kernel (see jacobi_fused_kernel): one word per boundary tile of a face -- (z chunks x tile rows)
+// for x faces, (z chunks x strips) for y faces, (tile rows x strips) for z faces; 16 x 64 = 1024 at 512^3 FP64
 #ifndef SB_FUSED_MAX_GROUPS
-#define SB_FUSED_MAX_GROUPS 1024
+#define SB_FUSED_MAX_GROUPS 4096
 #endif
 
-// Group counters and the ordering between ranks inside the fused kernel.  All pointers are device addresses.
+// Ordering between ranks inside the fused kernel.  All pointers are device addresses.
 struct FusedSync {
-  uint32_t *counters;            // [6][SB_FUSED_MAX_GROUPS] arrival counters, zero between launches (null: the library's per-stream block)
-  const uint32_t *wait_row[6];   // per face: this GPU's mailbox row [group] written by the neighbour across that face (null: no wait)
-  uint32_t *signal_row[6];       // per face: the neighbour's mailbox row [group] for this subdomain (null: neighbour ordered by stream events)
+  const uint32_t *wait_row[6];   // per face: this GPU's mailbox row [tile] written by the neighbour across that face (null: no wait)
+  uint32_t *signal_row[6];       // per face: the neighbour's mailbox row [tile] for this subdomain (null: neighbour ordered by stream events)
   uint32_t wait_value, signal_value;
-  int zrot, any_wait;            // set by the launcher
+  int zrot, any_wait, any_signal; // set by the launcher
 };
 
 // Up to 8 thin regions (the exterior slabs of one subdomain) updated by ONE launch.

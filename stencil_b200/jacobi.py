@@ -485,6 +485,48 @@ class Jacobi3D:
         self._ev_fused = events
         dd.swap()
 
+    def capture_fused(self, iterations: int = 2):
+        """Capture `iterations` (even: both swap parities) fused iterations into ONE CUDA graph and return it; `graph.replay()`
+        then advances the solution by that many iterations with a single launch from the host (the
+        reference captures its pack kernels the same way, src/packer.cu:96-106).  Single-process runs only: across ranks the
+        iteration number travels in the kernel arguments.  The Python-side swap state is unchanged by a replay (the parity
+        returns to where it was), so step_fused() / step() may be mixed with replays freely."""
+        import torch
+
+        if iterations < 2 or iterations % 2:
+            raise ValueError("capture an even number of iterations (both swap parities)")
+        if self.dd._remote is not None:
+            raise RuntimeError("capture_fused: single-process runs only (the cross-rank handshake passes the iteration number by value)")
+        self.step_fused()  # builds the argument packs, fills the ghost cells, allocates the group counters (no allocation may happen during capture)
+        self.step_fused()
+        if not self.fused_supported:
+            raise RuntimeError("capture_fused: the fused schedule does not apply to this domain")
+        self.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        s0 = self.streams[0]
+        with torch.cuda.graph(graph, stream=s0):
+            # the other subdomains' streams join the capture through the event dependencies step_fused records
+            for o in self.streams[1:]:
+                o.wait_stream(s0)
+            self._ev_fused = None
+            for _ in range(iterations):
+                self.step_fused()
+            for o in self.streams[1:]:
+                s0.wait_stream(o)
+        self._ev_fused = None  # events recorded during capture are not waitable outside it; replays are ordered by s0
+
+        class _FusedGraph:
+            """replay() launches the captured iterations on the solver's own stream (ordered with step_fused / synchronize)."""
+
+            def __init__(self, g, stream, iters):
+                self.graph, self.stream, self.iterations = g, stream, iters
+
+            def replay(self):
+                with torch.cuda.stream(self.stream):
+                    self.graph.replay()
+
+        return _FusedGraph(graph, s0, iterations)
+
     def close(self) -> None:
         """Drain the queued work; release the dense x receive arrays and mailboxes of the fused schedule."""
         self.synchronize()

@@ -18,8 +18,15 @@ from stencil_b200 import astaroth as ac
 pytestmark = pytest.mark.gpu
 
 
+def tma_applies(dtype, raw) -> bool:
+    """The TMA-fed team kernel needs FP64 and rows that are a multiple of 16 bytes (an even number of doubles)."""
+    return np.dtype(dtype) == np.float64 and raw[0] % 2 == 0
+
+
 def run_gpu(step, fin, fout, lo, hi, params, variant):
     """fin / fout: lists of 8 host arrays; returns the 8 updated `out` arrays."""
+    if variant in (ac.TEAM_TMA, ac.TEAM3_TMA) and not tma_applies(fin[0].dtype, fin[0].shape[::-1]):
+        pytest.skip("TMA-fed kernel: FP64 with an even row length only")
     din = [DevArray(a) for a in fin]
     dout = [DevArray(a) for a in fout]
     mz, my, mx = fin[0].shape
@@ -51,7 +58,7 @@ BOXES = [
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("variant", [ac.AUTO, ac.CELL, ac.TILE, ac.TEAM])
+@pytest.mark.parametrize("variant", [ac.AUTO, ac.CELL, ac.TILE, ac.TEAM, ac.TEAM_TMA, ac.TEAM3_TMA])
 @pytest.mark.parametrize("box", BOXES, ids=[f"{b[0]}-{b[1]}-{b[2]}" for b in BOXES])
 def test_substeps_match_oracle(dtype, variant, box):
     raw, lo, hi = box
@@ -72,13 +79,15 @@ def test_substeps_match_oracle(dtype, variant, box):
         assert np.array_equal(a[m], b[m])
 
 
-@pytest.mark.parametrize("variant", [ac.CELL, ac.TILE, ac.TEAM])
+@pytest.mark.parametrize("variant", [ac.CELL, ac.TILE, ac.TEAM, ac.TEAM_TMA, ac.TEAM3_TMA])
 @pytest.mark.parametrize("shape", [0, 1])
 def test_tile_shapes_and_zchunks(variant, shape, monkeypatch):
     """Both tile shapes per precision (SB_AC_SHAPE) and a forced short z chunk (ring warm-up at every chunk start)."""
     monkeypatch.setenv("SB_AC_SHAPE", str(shape))
     monkeypatch.setenv("SB_AC_ZCHUNK", "5")
     for dtype in (np.float64, np.float32):
+        if variant in (ac.TEAM_TMA, ac.TEAM3_TMA) and dtype == np.float32:
+            continue
         raw, lo, hi = (50, 45, 29), (3, 3, 3), (47, 42, 26)
         fields = make_fields(raw, seed=11, dtype=dtype)
         fin, fout = fields[:8], fields[8:]
@@ -89,7 +98,7 @@ def test_tile_shapes_and_zchunks(variant, shape, monkeypatch):
 
 
 @pytest.mark.skipif(not os.path.exists(GOLDEN), reason="golden vectors not generated yet (oracle/ref/make_astaroth_golden.py)")
-@pytest.mark.parametrize("variant", [ac.CELL, ac.TILE, ac.TEAM])
+@pytest.mark.parametrize("variant", [ac.CELL, ac.TILE, ac.TEAM, ac.TEAM_TMA, ac.TEAM3_TMA])
 def test_matches_reference_kernel_golden(variant):
     """The reference's own solve<0,1,2> (astaroth/kernels.cu, compiled unmodified for sm_100a) produced these."""
     z = np.load(GOLDEN)
@@ -107,7 +116,8 @@ def test_matches_reference_kernel_golden(variant):
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("ndom", [1, 2])
 @pytest.mark.parametrize("overlap", [True, False])
-def test_iteration_through_distributed_domain(dtype, ndom, overlap):
+@pytest.mark.parametrize("variant", [ac.AUTO, ac.TEAM])
+def test_iteration_through_distributed_domain(dtype, ndom, overlap, variant):
     """astaroth/astaroth.cu:551-640: per substep interior || exchange -> exterior; swap after the third.  Two
     iterations on 24x20x28 split over `ndom` subdomains, against oracle exchange + oracle solve."""
     import torch
@@ -139,7 +149,8 @@ def test_iteration_through_distributed_domain(dtype, ndom, overlap):
                         nxt[i][q][...] = host
         params = ac.conf_params(dt=1e-3)
         op = co.astaroth_conf_params(1e-3)
-        sim = ac.Astaroth(dd, handles, params, overlap=overlap)
+        # (LocalDomain places FP64 r=3 allocations 8 bytes into their block: the TMA-fed kernel's shifted tensor base)
+        sim = ac.Astaroth(dd, handles, params, overlap=overlap, variant=variant)
         for it in range(2):
             sim.step()
             for sub in range(3):

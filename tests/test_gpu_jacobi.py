@@ -306,3 +306,37 @@ def test_jacobi_vs_reference_kernel_golden(schedule):
                 assert float(np.abs(got.astype(np.float64) - fast).max()) <= 6e-8 * target + 1e-12  # <= 1 ulp per iteration (fast divide)
         finally:
             dd.close()
+
+
+@pytest.mark.parametrize("ndom", [1, 2])
+def test_fused_iterations_as_a_cuda_graph(ndom):
+    """Jacobi3D.capture_fused: 4 fused iterations captured into one CUDA graph; 3 replays (+ the 2 warm-up iterations the
+    capture runs) must equal 14 iterations of Jacobi3D.step bit for bit, and fused steps may follow a replay."""
+    from stencil_b200.jacobi import Jacobi3D, jacobi_radius
+
+    fields = []
+    for mode in ("sync", "graph"):
+        dd = sb.DistributedDomain(128, 64, 64)
+        dd.set_gpus([0] * ndom)
+        dd.set_radius(jacobi_radius())
+        h = dd.add_data(np.float64, "d")
+        dd.realize()
+        try:
+            jac = Jacobi3D(dd, h)
+            jac.init(0.5)
+            if mode == "sync":
+                for _ in range(16):
+                    jac.step()
+            else:
+                g = jac.capture_fused(4)  # runs 2 iterations itself
+                for _ in range(3):
+                    g.replay()
+                jac.synchronize()
+                jac.step_fused()
+                jac.step_fused()
+            jac.synchronize()
+            fields.append([d.interior_to_host(0) for d in dd.domains()])
+        finally:
+            dd.close()
+    for a, b in zip(*fields):
+        assert np.array_equal(a, b)
