@@ -56,6 +56,25 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(fused, n, dtype):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu summary (profiles/), with the file's hash so that
+    a stale citation is detectable."""
+    import hashlib
+
+    if n != 512 or dtype != "f64":
+        return {"traffic": None, "traffic_source": None}
+    name = "jacobi_fused_r2.summary.txt" if fused else "jacobi_march_r1.summary.txt"
+    path = os.path.join(ROOT, "profiles", name)
+    try:
+        text = open(path).read()
+        for ln in text.splitlines():
+            if ln.startswith("traffic = dram read + write (bytes)"):
+                return {"traffic": int(float(ln.split()[-1])), "traffic_source": {"file": "profiles/" + name, "sha256": hashlib.sha256(text.encode()).hexdigest()[:16]}}
+    except OSError:
+        pass
+    return {"traffic": None, "traffic_source": None}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -383,7 +402,7 @@ def run_ours(args, rank, world):
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm",
-        "kernel": "jacobi_march_kernel<PUSH> (whole region + halo push)" if fused else ("jacobi_march_kernel (interior region)" if jac.overlap else "jacobi_march_kernel (whole region)"),
+        "kernel": "jacobi_fused_kernel (whole region + halo push + rank handshake)" if fused else ("jacobi_march_kernel (interior region)" if jac.overlap else "jacobi_march_kernel (whole region)"),
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
@@ -391,10 +410,9 @@ def run_ours(args, rank, world):
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes,
         "kernel_ms": kern_ms,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, from the committed `ncu --set full`
-        # captures (profiles/jacobi_fused_r1.summary.txt: 2.143 GB for the fused whole-region kernel, 0.998 x algorithmic;
-        # profiles/jacobi_march_r1.summary.txt: 2.118 GB for the interior kernel); not re-measured by this run
-        "traffic": (2143024000 if fused else 2118000000) if (n == 512 and args.dtype == "f64") else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, read from the committed `ncu --set full`
+        # summary named in traffic_source (not re-measured by this run; null when no capture of this configuration exists)
+        **ncu_traffic(fused, n, args.dtype),
         "step_frac_of_roofline": (2 * es * cells / ngpu) / (ms_step * 1e-3) / 1e9 / peak,
     }
 

@@ -36,7 +36,7 @@ for stage in "$@"; do
   echo "=== stage $stage (N=$N)"
   case $stage in
   tests) # the whole GPU suite
-    timeout 1700 python -m pytest tests -q -m gpu -x 2>&1 | tail -8 | tee "$F/pytest_gpu.txt" ;;
+    timeout 1700 python -m pytest tests -q -m gpu -x 2>&1 | tail -70 | tee "$F/pytest_gpu.txt" | cut -c1-220 ;;
   tests_jacobi)
     timeout 900 python -m pytest tests/test_gpu_jacobi.py -q -m gpu -x 2>&1 | tail -40 | tee "$F/pytest_jacobi.txt" | cut -c1-250 ;;
   tests_mp) # multi-rank / multi-GPU parity (python one-process-per-GPU + in-process, C++ ranks under sb_mpirun)
@@ -66,6 +66,9 @@ for stage in "$@"; do
   ncu_fused2) # the fused kernel of the 2-subdomain stand-in (half of its CTAs are boundary CTAs) under ncu
     ONLY=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:jacobi_fused -s 12 -c 2 -o "$F/prof_jacobi_fused2" -f python scripts/time_fused.py 512 4 >"$F/ncu_fused2.log" 2>&1
     tail -3 "$F/ncu_fused2.log" ;;
+  debug_astaroth)
+    CUDA_LAUNCH_BLOCKING=1 timeout 600 python -m pytest tests/test_gpu_astaroth.py -q -m gpu -x -k "iteration_through" 2>&1 | tail -70 | cut -c1-220
+    timeout 600 python -m pytest tests/test_gpu_astaroth.py -q -m gpu -x 2>&1 | tail -70 | cut -c1-220 ;;
   tests_astaroth)
     timeout 900 python -m pytest tests/test_gpu_astaroth.py -q -m gpu -x 2>&1 | tail -60 | tee "$F/pytest_astaroth.txt" | cut -c1-250 ;;
   bench_launchsync) # the round-1 handshake (separate wait / signal launches) for the before/after

@@ -56,6 +56,29 @@ struct DeviceGuard {
   }
 };
 
+// The compute entry points take pointers and a stream but no device: the launch must happen on the device that owns the
+// memory (and the stream), whatever the calling thread's current device is -- a caller that drives several GPUs (or a test
+// that ran on another GPU before) would otherwise get "invalid resource handle" from the launch.
+int device_of(const void *ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+struct PtrDeviceGuard {
+  int prev = -1;
+  explicit PtrDeviceGuard(const void *ptr) {
+    const int dev = device_of(ptr);
+    int cur = -1;
+    if (dev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess) prev = cur;
+  }
+  ~PtrDeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 Dim3 d3(const int64_t v[3]) { return Dim3(v[0], v[1], v[2]); }
 void put(const Dim3 &d, int64_t out[3]) {
   out[0] = d.x;
@@ -521,6 +544,7 @@ int sb_exterior(const int64_t lo[3], const int64_t hi[3], const int64_t radius27
 
 // ----------------------------------------------------------------------------------------- box copies
 static int one_shot(const sb_box_copy &c, void *stream) {
+  PtrDeviceGuard guard(c.src.ptr); // launch where the source lives
   std::vector<sb::Seg> segs;
   int rc = build_segments(c, segs);
   if (rc != SB_OK) return rc;
@@ -706,6 +730,7 @@ static int jacobi_common(sb::JacobiParams &p, const sb_pitched &dst, const sb_pi
 int sb_jacobi3d_regions(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], int n, const int64_t *lo,
                         const int64_t *hi, const int64_t clo[3], const int64_t chi[3], void *stream) {
   if (n < 0 || n > 8) return fail(SB_ERR_INVALID, "between 0 and 8 regions per launch");
+  PtrDeviceGuard guard(dst.ptr);
   sb::JacobiParams p{};
   sb::JacobiRegions r{};
   int zmax = 0;
@@ -742,6 +767,7 @@ int sb_jacobi3d_regions(sb_pitched dst, sb_pitched src, int dtype_size, const in
 
 int sb_jacobi3d(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3],
                 const int64_t hi[3], const int64_t clo[3], const int64_t chi[3], void *stream) {
+  PtrDeviceGuard guard(dst.ptr);
   sb::JacobiParams p{};
   int rc = to_alloc_box(src, dtype_size, acc_origin, lo, hi, p.lo, p.hi);
   if (rc != SB_OK) return rc;
@@ -771,6 +797,7 @@ int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int6
 int sb_jacobi3d_fused_sync(sb_pitched dst, sb_pitched src, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3], const int64_t hi[3],
                            const int64_t clo[3], const int64_t chi[3], const sb_halo_push *push, const sb_step_sync *sync, void *stream) {
   if (!push) return fail(SB_ERR_INVALID, "null push table");
+  PtrDeviceGuard guard(dst.ptr);
   sb::FusedSync fs{};
   if (sync) {
     for (int f = 0; f < 6; ++f) {
@@ -843,6 +870,7 @@ int sb_astaroth_substep(int step, const void *const in[8], void *const out[8], i
   if (!in || !out || !raw || !lo || !hi || !params) return fail(SB_ERR_INVALID, "null argument");
   if (step < 0 || step > 2) return fail(SB_ERR_INVALID, "substep %d (Williamson RK3 has substeps 0, 1, 2)", step);
   if (dtype_size != 4 && dtype_size != 8) return fail(SB_ERR_INVALID, "dtype_size %d (4 = float, 8 = double)", dtype_size);
+  PtrDeviceGuard guard(out[0]);
   if (variant < 0 || variant > 5) return fail(SB_ERR_INVALID, "variant %d", variant);
   sb::AcFields f;
   for (int i = 0; i < sb::kAcFields; ++i) {
@@ -871,6 +899,7 @@ int sb_astaroth_substep(int step, const void *const in[8], void *const out[8], i
 
 int sb_fill(sb_pitched dst, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3], const int64_t hi[3], double value,
             void *stream) {
+  PtrDeviceGuard guard(dst.ptr);
   int alo[3], ahi[3];
   int rc = to_alloc_box(dst, dtype_size, acc_origin, lo, hi, alo, ahi);
   if (rc != SB_OK) return rc;
@@ -882,6 +911,7 @@ int sb_fill(sb_pitched dst, int dtype_size, const int64_t acc_origin[3], const i
 
 int sb_sqdiff(sb_pitched a, sb_pitched b, int dtype_size, const int64_t acc_origin[3], const int64_t lo[3], const int64_t hi[3],
               double *out_dev, void *stream) {
+  PtrDeviceGuard guard(a.ptr);
   int alo[3], ahi[3];
   int rc = to_alloc_box(a, dtype_size, acc_origin, lo, hi, alo, ahi);
   if (rc != SB_OK) return rc;

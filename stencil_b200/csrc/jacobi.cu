@@ -77,7 +77,7 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // (pointer set-up before the loop), and the x neighbour of the first / last column may come from a dense received array
 // instead of the ghost column (EDGE = 3).  Nothing is pushed inside the loop: the faces are shipped afterwards by the
 // last CTA of each face group (jacobi_fused_kernel).
-template <typename T, int VX, int RY, bool SHIFT, int PUSH> // PUSH (= EDGE): 0 plain, 2 boundary CTA, 3 boundary CTA with dense x ghosts
+template <typename T, int VX, int RY, bool SHIFT, int PUSH> // PUSH (= EDGE): 0 plain, 1 boundary CTA that pushes nothing (all faces read in place), 2 boundary CTA, 3 boundary CTA with dense x ghosts
 __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, const int by, const int bz, const bool wait_barrier = false) {
   static_assert(!SHIFT || (RY == 1 && VX >= 2), "the phase-shifted variant handles one row per warp");
   static_assert(!PUSH || RY == 1, "the push variant handles one row per warp");
@@ -167,13 +167,13 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   //  y faces: the warp that owns the first / last row stores its vector a second time, into the neighbour's ghost row,
   //           through a loop-invariant address difference (one predicated vector store per step).
   //  z faces: the last plane of the chunk is still in registers after the loop; the first one is re-read (own store).
-  __shared__ T xstage[PUSH ? 2 : 1][PUSH ? 8 : 1][PUSH ? 32 : 1];
+  __shared__ T xstage[PUSH >= 2 ? 2 : 1][PUSH >= 2 ? 8 : 1][PUSH >= 2 ? 32 : 1];
   int xsi = -1;       // which element of this lane's vector is an x-face cell (-1: none; a lane never holds both faces: ex >= 16)
   T *xsp = nullptr;   // where that cell of the current plane is parked
   long long ydiff = 0;
   bool ypush = false, ypost = false;
   int ydir = -1;
-  if (PUSH && row_ok[0]) {
+  if (PUSH >= 2 && row_ok[0]) {
 #pragma unroll
     for (int i = 0; i < VX; ++i) {
       if (x + i == p.lo[0] && p.push_ptr[0]) xsi = i, xsp = &xstage[0][warp][0];
@@ -190,7 +190,7 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
     }
   }
   // a one-row subdomain faces both y neighbours: the second side goes the slow way
-  const bool ypost_hi = PUSH && row_ok[0] && ydir == 2 && y == p.hi[1] - 1 && p.push_ptr[3];
+  const bool ypost_hi = PUSH >= 2 && row_ok[0] && ydir == 2 && y == p.hi[1] - 1 && p.push_ptr[3];
 
   // boundary CTAs of the fused kernel: the flag poll issued before all this set-up must have completed before any load
   if (wait_barrier) __syncthreads();
@@ -276,7 +276,7 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
             if (cell_ok & (1u << i)) reinterpret_cast<T *>(pw[j])[i] = out.v[i];
         }
       }
-      if (PUSH) {
+      if (PUSH >= 2) {
         if (xsi >= 0) {
           T v = out.v[0];
 #pragma unroll
@@ -307,7 +307,7 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
     step(C, A, B);
   }
 
-  if (PUSH) {
+  if (PUSH >= 2) {
     const long long es = (long long)sizeof(T);
     const int np = z1 - z0;
     // x faces: the staged column of this row, one plane per lane
@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(256, MB) jacobi_march_kernel(const __grid_cons
 //    and "the neighbour's tile is done reading the ghost cells I am about to overwrite".  Neighbours walk their grids in
 //    the same order, so the word was written a whole iteration earlier: x / y tiles by construction, z tiles because the
 //    z order is rotated by half the chunks (s.zrot) -- without the rotation the first chunk of iteration e+1 would need
-//    what the last chunk of iteration e ships.  ONE thread polls with relaxed loads and fences once: every acquire
-//    (ld.acquire, fence.acq_rel) also invalidates the SM's whole L1 (CCTL.IVALL), which stalls the co-resident CTAs.
+//    what the last chunk of iteration e ships.  ONE thread polls (ld.acquire.sys); every acquire also invalidates the
+//    SM's whole L1 (CCTL.IVALL), which costs the co-resident CTAs an L2 round trip, so there is exactly one per face.
 constexpr int kMaxGroups = SB_FUSED_MAX_GROUPS;
 
 // mailbox word of the tile (bx, by, bz) on face f: the same arithmetic on both sides of the face (neighbours across a
@@ -437,10 +437,14 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
   const bool waits = s.any_wait && faces;
   if (waits && threadIdx.x == 0) {
     const uint32_t want = s.wait_value;
+    // ld.acquire.sys = LDG.STRONG.SYS + CCTL.IVALL (the SM's L1 is dropped, so that ghost cells fetched before the
+    // neighbour wrote them cannot be served from it).  Measured alternatives: relaxed loads + one fence.acq_rel.sys cost
+    // 32 us per iteration at N = 2 (MEMBAR.ALL.SYS at the start of every boundary CTA), three acquiring threads nothing more
+    // than one.
     auto poll = [&](const uint32_t *slot) {
       uint32_t v;
       while (true) {
-        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
         if ((int32_t)(v - want) >= 0) break; // wrap-safe "v >= want"
         __nanosleep(100);
       }
@@ -454,7 +458,6 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
         if (bx + 1 < nx) poll(s.wait_row[f] + tile_slot(f, bx + 1, by, bz, nx, ny));
       }
     }
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
   }
 
   march_body<T, VX, 1, SHIFT, EDGE>(p, bx, by, bz, waits); // pushes this tile's face cells as it goes
@@ -489,7 +492,8 @@ template <typename T, int VX, bool SHIFT> __device__ __noinline__ void signal_ti
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
   if (threadIdx.x == 0) {
-    __threadfence_system(); // every warp's pushes have landed in the neighbour before the flag does
+    // st.release.sys: every warp's pushes (ordered before this point by the barrier) have landed in the neighbour before
+    // the flag does; no separate __threadfence_system() (measured: a second MEMBAR.SYS per boundary CTA)
     const uint32_t value = s.signal_value;
 #pragma unroll
     for (int f = 0; f < 6; ++f)
@@ -659,7 +663,13 @@ template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p
   const bool regs56 = env_int("SB_FUSED_REGS", 56) == 56;
   const bool split = env_int("SB_FUSED_SPLIT", 1) != 0;
   const bool dense_ghosts = p.xghost_ptr[0] || p.xghost_ptr[1];
+  bool any_push = false;
+  for (int f = 0; f < 6; ++f) any_push = any_push || p.push_ptr[f];
   auto go = [&](auto kern) { kern<<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z); };
+  if (!any_push && !dense_ghosts) { // every face is a periodic self-neighbour read in place (one GPU): no push code in the loop
+    split ? go(jacobi_fused_kernel<T, VX, SHIFT, 1, true>) : go(jacobi_fused_kernel<T, VX, SHIFT, 1, false>);
+    return 1;
+  }
   if (regs56) {
     if (dense_ghosts) split ? go(jacobi_fused_kernel56<T, VX, SHIFT, 3, true>) : go(jacobi_fused_kernel56<T, VX, SHIFT, 3, false>);
     else split ? go(jacobi_fused_kernel56<T, VX, SHIFT, 2, true>) : go(jacobi_fused_kernel56<T, VX, SHIFT, 2, false>);
