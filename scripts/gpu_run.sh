@@ -57,8 +57,11 @@ for stage in "$@"; do
   bench_queued)
     bench queued --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --schedule queued --no-parity ;;
   bench_diag) # where the multi-rank overhead of the fused kernel goes (timing only: some of these compute wrong halos)
-    SB_FUSED_REGS=64 bench regs64 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
+    bench again --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
     SB_DEBUG_FUSED=1 bench nowait --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
+    SB_DEBUG_FUSED=3 bench nowait_nosignal --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
+    SB_DEBUG_NOPUSH=1 bench nopush --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity ;;
+  bench_diag2)
     SB_DEBUG_FUSED=3 bench nowait_nosignal --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
     SB_DEBUG_NOPUSH=1 bench nopush --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity ;;
   time_fused) # kernel variants + single-GPU stand-ins for the multi-rank kernels, one box
@@ -69,6 +72,13 @@ for stage in "$@"; do
   debug_astaroth)
     CUDA_LAUNCH_BLOCKING=1 timeout 600 python -m pytest tests/test_gpu_astaroth.py -q -m gpu -x -k "iteration_through" 2>&1 | tail -70 | cut -c1-220
     timeout 600 python -m pytest tests/test_gpu_astaroth.py -q -m gpu -x 2>&1 | tail -70 | cut -c1-220 ;;
+  ncu_nvlink) # NVLink byte counters of the exchange kernel and of the fused jacobi kernel, 1 process x 2 GPUs (needs >= 2 GPUs)
+    timeout 600 ncu --metrics nvltx__bytes.sum,nvlrx__bytes.sum,gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:box_copy -s 10 -c 8 --csv --log-file "$F/nvlink_box_copy.csv" python scripts/time_exchange_mg.py 256 2 3 float32 >"$F/nvlink_box_copy.log" 2>&1
+    tail -9 "$F/nvlink_box_copy.csv" | cut -c1-260
+    NGPU=2 ONLY=2 timeout 600 ncu --metrics nvltx__bytes.sum,nvlrx__bytes.sum,gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:jacobi_fused -s 8 -c 4 --csv --log-file "$F/nvlink_fused.csv" python scripts/time_fused.py 512 4 >"$F/nvlink_fused.log" 2>&1
+    tail -5 "$F/nvlink_fused.csv" | cut -c1-260 ;;
+  tma_pack) # TMA 3-D pack experiment vs the LSU path (scripts/exp/tma_pack3d.cu, built in the container)
+    timeout 120 scripts/exp/tma_pack3d 2>&1 | tail -12 | tee "$F/tma_pack3d.txt" ;;
   tests_astaroth)
     timeout 900 python -m pytest tests/test_gpu_astaroth.py -q -m gpu -x 2>&1 | tail -60 | tee "$F/pytest_astaroth.txt" | cut -c1-250 ;;
   bench_launchsync) # the round-1 handshake (separate wait / signal launches) for the before/after

@@ -19,9 +19,10 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 dtype = np.float64 if os.environ.get("DTYPE", "f64") == "f64" else np.float32
 
 
-def run(ndom, label, fused=True):
-    dd = sb.DistributedDomain(n, n, n)
-    dd.set_gpus([0] * ndom)
+def run(ndom, label, fused=True, shape=None):
+    dd = sb.DistributedDomain(*(shape or (n, n, n)))
+    ngpu = int(os.environ.get("NGPU", "1"))  # NGPU=2: the subdomains alternate between two GPUs of this process (NVLink pushes)
+    dd.set_gpus([i % ngpu for i in range(ndom)])
     dd.set_radius(jacobi_radius())
     h = dd.add_data(dtype)
     dd.realize()
@@ -39,7 +40,8 @@ def run(ndom, label, fused=True):
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) / reps * 1e3
     es = np.dtype(dtype).itemsize
-    print(f"{label:46s} {ms:.4f} ms/step  {2*es*n**3/ms/1e6:.0f} GB/s", flush=True)
+    cells = int(np.prod(shape)) if shape else n**3
+    print(f"{label:58s} {ms:.4f} ms/step  {ms * n**3 / cells:.4f} ms per {n}^3  {2*es*cells/ms/1e6:.0f} GB/s", flush=True)
     jac.close()
     dd.close()
     return ms
@@ -50,6 +52,17 @@ if only:
     run(int(only), f"fused (default variant) subdomains={only}")
     sys.exit(0)
 run(1, "plain whole-region kernel (calibration)", fused=False)
+if os.environ.get("SPLITS", "1") == "1":
+    # which face direction costs what: two 512^3 subdomains on this GPU, cut along x / y / z (the other two axes wrap in place)
+    run(2, "fused, 2 x 512^3 cut along x (dense x lines)", shape=(2 * n, n, n))
+    run(2, "fused, 2 x 512^3 cut along y", shape=(n, 2 * n, n))
+    run(2, "fused, 2 x 512^3 cut along z", shape=(n, n, 2 * n))
+    run(8, "fused, 8 x 512^3 cut along x, y and z", shape=(2 * n, 2 * n, 2 * n))
+    os.environ["SB_DEBUG_NOPUSH"] = "1"
+    run(2, "fused, 2 x 512^3 cut along x NOPUSH", shape=(2 * n, n, n))
+    run(8, "fused, 8 x 512^3 cut along x, y and z NOPUSH", shape=(2 * n, 2 * n, 2 * n))
+    del os.environ["SB_DEBUG_NOPUSH"]
+    sys.exit(0)
 for nopush in ("", "1"):
     if nopush:
         os.environ["SB_DEBUG_NOPUSH"] = "1"  # timing only: nothing is shipped (results wrong)

@@ -60,6 +60,20 @@ template <typename T> __device__ __forceinline__ T stencil_value(T px, T mx, T p
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// x-face cells of a boundary tile, parked while it marches (fused kernel): [side][warp = row][plane of the chunk]
+__shared__ unsigned long long g_xstage[2 * 8 * 32];
+template <typename T> __device__ __forceinline__ T *xstage_row(int side, int warp) { return reinterpret_cast<T *>(g_xstage) + (side * 8 + warp) * 32; }
+
+// May the warp owning a y-face row store it into the neighbour from inside the loop?  Only if every lane can store its
+// whole vector, aligned, and the neighbour's planes are as far apart as ours; anything else (odd sizes, phase-shifted FP32
+// rows) is copied after the march from the warp's own stores.  (Asked before the march and again after it.)
+template <typename T, int VX>
+__device__ __forceinline__ bool y_store_in_loop(const JacobiParams &p, int ydir, int x, int z0, bool full, unsigned cell_ok) {
+  const unsigned long long t = (unsigned long long)(p.push_ptr[ydir] + (long long)x * (long long)sizeof(T) + (long long)z0 * p.slice);
+  const bool ok = p.push_slice[ydir] == p.slice && (t % (sizeof(T) * VX)) == 0 && (full || !cell_ok);
+  return __all_sync(0xffffffffu, ok);
+}
+
 // Register-blocked z-march (see the file header).  Everything that does not change along z is hoisted
 // out of the loop -- clamped row offsets, store masks, the (y - cy)^2 term of the sphere test -- so a
 // z-step is: RY centre loads for plane z+1, 2 halo-row loads and RY edge scalars for plane z, the
@@ -72,15 +86,27 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // loads, stores) stay full 128-bit vectors on every row; only the two L1-resident neighbour rows
 // (y-1, y+1), which have the opposite phase, are fetched as two half vectors.
 //
-// EDGE variants (RY = 1; the boundary CTAs of the fused kernel): identical to the plain loop except for where the cells
-// just outside the subdomain come from -- a periodic self-neighbour is read in place from the opposite face of src
-// (pointer set-up before the loop), and the x neighbour of the first / last column may come from a dense received array
-// instead of the ghost column (EDGE = 3).  Nothing is pushed inside the loop: the faces are shipped afterwards by the
-// last CTA of each face group (jacobi_fused_kernel).
-template <typename T, int VX, int RY, bool SHIFT, int PUSH> // PUSH (= EDGE): 0 plain, 1 boundary CTA that pushes nothing (all faces read in place), 2 boundary CTA, 3 boundary CTA with dense x ghosts
+// Boundary variants (RY = 1; the boundary CTAs of the fused kernel), MODE bits:
+//   1 EDGE   the cells just outside the subdomain may come from somewhere else -- a periodic self-neighbour is read in place
+//            from the opposite face of src (pointer set-up before the loop; along z the last step of the top chunk is taken
+//            out of the loop) -- and the z faces of the tile are copied to the neighbour after the march.  The loop itself is
+//            the plain one.
+//   2 XPUSH  the x neighbour of the first / last column may come from a dense received array, and the tile's own x-face
+//            cells are parked in shared memory as the march goes (one predicated STS per step).
+//   4 YPUSH  the warp that owns a y-face row stores it a second time, into the neighbour (one predicated STG per step).
+//   8 ZWRAP  a tile of the top chunk whose +z neighbour is the subdomain itself: pc jumps down to the bottom plane before
+//            the last step (one test per step).
+// The kernel is latency- and issue-bound at once (53 % issue utilisation with 8 warps per scheduler): every instruction
+// added to the loop shows in the run time, so each boundary CTA runs the leanest variant that serves its faces.
+template <typename T, int VX, int RY, bool SHIFT, int MODE>
 __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, const int by, const int bz, const bool wait_barrier = false) {
   static_assert(!SHIFT || (RY == 1 && VX >= 2), "the phase-shifted variant handles one row per warp");
-  static_assert(!PUSH || RY == 1, "the push variant handles one row per warp");
+  static_assert(!MODE || RY == 1, "the boundary variants handle one row per warp");
+  static_assert(MODE == 0 || (MODE & 1), "XPUSH / YPUSH imply EDGE");
+  constexpr bool EDGE = (MODE & 1) != 0; // EDGE
+  constexpr bool XP = (MODE & 2) != 0;
+  constexpr bool YP = (MODE & 4) != 0;
+  constexpr bool ZW = (MODE & 8) != 0;
   using V = Vec<T, VX>;
   constexpr int WY = 8; // warps stacked in y
   const int lane = threadIdx.x & 31;
@@ -114,7 +140,7 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   const bool edge_lane = (lane == 0) || (lane == 31);
   long long phstep = S; // per-plane advance of ph (mode 3: a dense x-ghost array is z fastest)
   int hxv = lane == 0 ? x - 1 : x + VX;
-  if (PUSH && p.xwrap) { // periodic self-neighbour: the cell beyond a face is the first / last cell of the same row
+  if (EDGE && p.xwrap) { // periodic self-neighbour: the cell beyond a face is the first / last cell of the same row
     if (hxv == p.lo[0] - 1) hxv = p.hi[0] - 1;
     else if (hxv == p.hi[0]) hxv = p.lo[0];
   }
@@ -123,7 +149,7 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   for (int j = 0; j < RY; ++j) {
     pc[j] = src + (long long)(z0 + 1) * S + yo(y + j) + xoff;
     ph[j] = src + (long long)z0 * S + yo(y + j) + (long long)hx * (long long)sizeof(T);
-    if (PUSH == 3) { // the x neighbour of the first / last compute cell may come from a dense received array [y][z]
+    if (XP) { // the x neighbour of the first / last compute cell may come from a dense received array [y][z]
       const int side = (lane == 0 && x == p.lo[0]) ? 0 : ((lane == 31 && x + VX == p.hi[0]) ? 1 : -1);
       if (side >= 0 && p.xghost_ptr[side]) {
         ph[j] = p.xghost_ptr[side] + (long long)(y + j) * p.xghost_pitch[side] + (long long)z0 * (long long)sizeof(T);
@@ -133,12 +159,34 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
     pw[j] = p.dst + (long long)z0 * S + (long long)(y + j) * P + (long long)x * (long long)sizeof(T);
   }
   int yu = y - 1, yd = y + RY;
-  if (PUSH && p.ywrap) { // periodic self-neighbour: the row beyond a face is the opposite face row
+  if (EDGE && p.ywrap) { // periodic self-neighbour: the row beyond a face is the opposite face row
     if (yu == p.lo[1] - 1) yu = p.hi[1] - 1;
     if (yd == p.hi[1]) yd = p.lo[1];
   }
   const char *pu = src + (long long)z0 * S + yo(yu) + xoff; // row above the strip, plane z
   const char *pd = src + (long long)z0 * S + yo(yd) + xoff; // row below the strip, plane z
+
+  // SHIFT + periodic self-neighbour along x: on phase-shifted rows the ghost cell just outside a face sits INSIDE a lane's
+  // vector (the strip starts VX / 2 cells early), where the edge lanes' scalar cannot replace it: that element is patched
+  // at load time with the cell of the opposite face (one predicated scalar load per step for two lanes of such a row)
+  int wrap_i = -1;
+  const char *wrap_p = nullptr; // the wrapped cell of plane z+1
+  if (EDGE && SHIFT && p.xwrap) {
+#pragma unroll
+    for (int i = 0; i < VX; ++i) {
+      const int xi = x + i;
+      const int xw = xi == p.lo[0] - 1 ? p.hi[0] - 1 : (xi == p.hi[0] ? p.lo[0] : -1);
+      if (xw >= 0) wrap_i = i, wrap_p = src + (long long)(z0 + 1) * S + yo(y) + (long long)xw * (long long)sizeof(T);
+    }
+  }
+  auto patch = [&](V &v, long long planes_back) {
+    if (EDGE && SHIFT && wrap_i >= 0) {
+      const T w = *reinterpret_cast<const T *>(wrap_p - planes_back * S);
+#pragma unroll
+      for (int i = 0; i < VX; ++i)
+        if (wrap_i == i) v.v[i] = w;
+    }
+  };
 
   // store masks
   bool row_ok[RY];
@@ -167,30 +215,25 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   //  y faces: the warp that owns the first / last row stores its vector a second time, into the neighbour's ghost row,
   //           through a loop-invariant address difference (one predicated vector store per step).
   //  z faces: the last plane of the chunk is still in registers after the loop; the first one is re-read (own store).
-  __shared__ T xstage[PUSH >= 2 ? 2 : 1][PUSH >= 2 ? 8 : 1][PUSH >= 2 ? 32 : 1];
+  //  Everything that happens after the march is in finish_tile, which derives its own indices: nothing of it is live here.
   int xsi = -1;       // which element of this lane's vector is an x-face cell (-1: none; a lane never holds both faces: ex >= 16)
   T *xsp = nullptr;   // where that cell of the current plane is parked
   long long ydiff = 0;
-  bool ypush = false, ypost = false;
-  int ydir = -1;
-  if (PUSH >= 2 && row_ok[0]) {
+  bool ypush = false;
+  if (XP && row_ok[0]) {
 #pragma unroll
     for (int i = 0; i < VX; ++i) {
-      if (x + i == p.lo[0] && p.push_ptr[0]) xsi = i, xsp = &xstage[0][warp][0];
-      if (x + i == p.hi[0] - 1 && p.push_ptr[1]) xsi = i, xsp = &xstage[1][warp][0];
-    }
-    ydir = (y == p.lo[1] && p.push_ptr[2]) ? 2 : ((y == p.hi[1] - 1 && p.push_ptr[3]) ? 3 : -1);
-    if (ydir >= 0) {
-      ydiff = (p.push_ptr[ydir] + (long long)x * (long long)sizeof(T) + (long long)z0 * S) - pw[0];
-      // in the loop only if every lane can store its whole vector, aligned, and the neighbour's planes are as far apart as
-      // ours; anything else (odd sizes, phase-shifted FP32 rows) is copied after the march from this warp's own stores
-      const bool ok = p.push_slice[ydir] == S && ((unsigned long long)(pw[0] + ydiff) % sizeof(V)) == 0 && (full || !cell_ok);
-      ypush = __all_sync(0xffffffffu, ok);
-      ypost = !ypush;
+      if (x + i == p.lo[0] && p.push_ptr[0]) xsi = i, xsp = xstage_row<T>(0, warp);
+      if (x + i == p.hi[0] - 1 && p.push_ptr[1]) xsi = i, xsp = xstage_row<T>(1, warp);
     }
   }
-  // a one-row subdomain faces both y neighbours: the second side goes the slow way
-  const bool ypost_hi = PUSH >= 2 && row_ok[0] && ydir == 2 && y == p.hi[1] - 1 && p.push_ptr[3];
+  if (YP && row_ok[0]) {
+    const int ydir = (y == p.lo[1] && p.push_ptr[2]) ? 2 : ((y == p.hi[1] - 1 && p.push_ptr[3]) ? 3 : -1);
+    if (ydir >= 0) {
+      ydiff = (p.push_ptr[ydir] + (long long)x * (long long)sizeof(T) + (long long)z0 * S) - pw[0];
+      ypush = y_store_in_loop<T, VX>(p, ydir, x, z0, full, cell_ok);
+    }
+  }
 
   // boundary CTAs of the fused kernel: the flag poll issued before all this set-up must have completed before any load
   if (wait_barrier) __syncthreads();
@@ -199,15 +242,19 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   for (int j = 0; j < RY; ++j) {
     // plane z0-1 (a periodic self-neighbour along z: the ghost plane below the subdomain is its own top plane, read in place)
     const char *pa = pc[j] - 2 * S;
-    if (PUSH && p.zwrap && z0 == p.lo[2]) pa += (long long)(p.hi[2] - p.lo[2]) * S;
+    if (EDGE && p.zwrap && z0 == p.lo[2]) pa += (long long)(p.hi[2] - p.lo[2]) * S;
     A[j] = *reinterpret_cast<const V *>(pa);
     B[j] = *reinterpret_cast<const V *>(pc[j] - S); // plane z0
+    patch(A[j], (EDGE && p.zwrap && z0 == p.lo[2]) ? 2 - (long long)(p.hi[2] - p.lo[2]) : 2);
+    patch(B[j], 1);
   }
-  // ... and the plane above the top one is the bottom plane: pc jumps down before the last step of the top chunk
-  const int zjump = (PUSH && p.zwrap && z1 == p.hi[2]) ? p.hi[2] - 1 : -1;
-  if (PUSH && zjump == z0) {
+  // ... and the plane above the top one is the bottom plane: pc jumps down before the last step of the top chunk (ZWRAP:
+  // only the CTAs of the top chunk carry the test)
+  const int zjump = (ZW && p.zwrap && z1 == p.hi[2]) ? p.hi[2] - 1 : -1;
+  if (ZW && zjump == z0) {
 #pragma unroll
     for (int j = 0; j < RY; ++j) pc[j] -= (long long)(p.hi[2] - p.lo[2]) * S;
+    if (SHIFT) wrap_p -= (long long)(p.hi[2] - p.lo[2]) * S;
   }
   const int zlast = p.raw[2] - 1; // last plane that may be touched (prefetch guard)
   int z = z0;
@@ -215,6 +262,10 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   auto step = [&](const V(&prev)[RY], const V(&cur)[RY], V(&nxt)[RY]) {
 #pragma unroll
     for (int j = 0; j < RY; ++j) nxt[j] = *reinterpret_cast<const V *>(pc[j]);
+    if (EDGE && SHIFT) {
+      patch(nxt[0], 0);
+      wrap_p += S;
+    }
     if (p.prefetch > 0 && z + 1 + p.prefetch <= zlast) {
 #pragma unroll
       for (int j = 0; j < RY; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc[j] + (long long)p.prefetch * S));
@@ -276,26 +327,25 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
             if (cell_ok & (1u << i)) reinterpret_cast<T *>(pw[j])[i] = out.v[i];
         }
       }
-      if (PUSH >= 2) {
-        if (xsi >= 0) {
-          T v = out.v[0];
+      if (XP && xsi >= 0) {
+        T v = out.v[0];
 #pragma unroll
-          for (int i = 1; i < VX; ++i)
-            if (xsi == i) v = out.v[i];
-          *xsp++ = v;
-        }
-        if (ypush && full) *reinterpret_cast<V *>(pw[j] + ydiff) = out;
+        for (int i = 1; i < VX; ++i)
+          if (xsi == i) v = out.v[i];
+        *xsp++ = v;
       }
+      if (YP && ypush && full) *reinterpret_cast<V *>(pw[j] + ydiff) = out;
       pc[j] += S;
-      ph[j] += (PUSH == 3) ? phstep : S;
+      ph[j] += XP ? phstep : S;
       pw[j] += S;
     }
     pu += S;
     pd += S;
     ++z;
-    if (PUSH && z == zjump) {
+    if (ZW && z == zjump) {
 #pragma unroll
       for (int j = 0; j < RY; ++j) pc[j] -= (long long)(p.hi[2] - p.lo[2]) * S;
+      if (SHIFT) wrap_p -= (long long)(p.hi[2] - p.lo[2]) * S;
     }
   };
 
@@ -305,59 +355,6 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
     step(B, C, A);
     if (z >= z1) break;
     step(C, A, B);
-  }
-
-  if (PUSH >= 2) {
-    const long long es = (long long)sizeof(T);
-    const int np = z1 - z0;
-    // x faces: the staged column of this row, one plane per lane
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const bool mine = xsi >= 0 && (side == 0 ? x + xsi == p.lo[0] : x + xsi == p.hi[0] - 1);
-      if (!__ballot_sync(0xffffffffu, mine)) continue; // warp-uniform
-      __syncwarp();
-      if (lane < np) {
-        char *t = p.xdense[side] ? p.push_ptr[side] + (long long)y * p.push_pitch[side] + (long long)(z0 + lane) * es
-                                 : p.push_ptr[side] + (long long)(z0 + lane) * p.push_slice[side] + (long long)y * p.push_pitch[side];
-        *reinterpret_cast<T *>(t) = xstage[side][warp][lane];
-      }
-    }
-    // z faces: this lane's own stores of the first / last plane of the chunk, read back (one load per lane; the z-face CTAs
-    // are 1 in 8 and, with the rotated z order, not the last ones of the grid)
-    if (row_ok[0] && cell_ok) {
-#pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        if (!(side == 0 ? z0 == p.lo[2] : z1 == p.hi[2]) || !p.push_ptr[4 + side]) continue;
-        const int zf = side == 0 ? z0 : z1 - 1;
-        const char *r = p.dst + (long long)zf * S + (long long)y * P + (long long)x * es;
-        char *t = p.push_ptr[4 + side] + (long long)y * p.push_pitch[4 + side] + (long long)x * es;
-        if (full && ((unsigned long long)t % sizeof(V)) == 0) {
-          V v;
-#pragma unroll
-          for (int i = 0; i < VX; ++i) v.v[i] = __ldcg(reinterpret_cast<const T *>(r) + i);
-          *reinterpret_cast<V *>(t) = v;
-        } else {
-#pragma unroll
-          for (int i = 0; i < VX; ++i)
-            if (cell_ok & (1u << i)) reinterpret_cast<T *>(t)[i] = __ldcg(reinterpret_cast<const T *>(r) + i);
-        }
-      }
-    }
-    // y faces the loop could not serve: copied from this lane's own stores, plane by plane
-    if (ypost || ypost_hi) {
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int d = k == 0 ? ydir : 3;
-        if (k == 0 ? !ypost : !ypost_hi) continue;
-        const char *r = p.dst + (long long)y * P + (long long)x * es;
-        char *t = p.push_ptr[d] + (long long)x * es;
-        for (int zz = z0; zz < z1; ++zz) {
-#pragma unroll
-          for (int i = 0; i < VX; ++i)
-            if (cell_ok & (1u << i)) reinterpret_cast<T *>(t + (long long)zz * p.push_slice[d])[i] = __ldcg(reinterpret_cast<const T *>(r + (long long)zz * S) + i);
-        }
-      }
-    }
   }
 }
 
@@ -403,9 +400,9 @@ __device__ __forceinline__ int tile_slot(int f, int bx, int by, int bz, int nx, 
   return f < 2 ? bz * ny + by : (f < 4 ? bz * nx + bx : by * nx + bx);
 }
 
-template <typename T, int VX, bool SHIFT> __device__ __noinline__ void signal_tile(const JacobiParams &p, const FusedSync &s, int nx, int ny, int nz);
+template <typename T, int VX, bool SHIFT> __device__ __noinline__ void finish_tile(const JacobiParams &p, const FusedSync &s, int nx, int ny, int nz);
 
-template <typename T, int VX, bool SHIFT, int EDGE, bool SPLIT>
+template <typename T, int VX, bool SHIFT, int EDGE>
 __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSync &s, int nx, int ny, int nz) {
   int b = blockIdx.x;
   const int bx = b % nx;
@@ -423,7 +420,7 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
   if (by == ny - 1) touch |= 8u;
   if (bz == 0) touch |= 16u;
   if (bz == nz - 1) touch |= 32u;
-  if (SPLIT && !touch) { // CTAs that touch no face take the plain loop (a second copy of the loop in the kernel)
+  if (!touch) { // CTAs that touch no face take the plain loop
     march_body<T, VX, 1, SHIFT, 0>(p, bx, by, bz);
     return;
   }
@@ -431,6 +428,9 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
 #pragma unroll
   for (int f = 0; f < 6; ++f)
     if ((touch >> f & 1u) && p.push_ptr[f]) faces |= 1u << f;
+  // the leanest loop that serves this tile's faces (march_body): x pushes or dense x ghosts, y pushes, or neither
+  const bool needx = EDGE >= 2 && (((touch & 1u) && (p.push_ptr[0] || p.xghost_ptr[0])) || ((touch & 2u) && (p.push_ptr[1] || p.xghost_ptr[1])));
+  const bool needy = EDGE >= 2 && (faces & 12u);
 
   // poll first, synchronise late: the barrier that publishes the poll to the other warps sits inside march_body, after its
   // address set-up and right before its first load
@@ -460,23 +460,104 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
     }
   }
 
-  march_body<T, VX, 1, SHIFT, EDGE>(p, bx, by, bz, waits); // pushes this tile's face cells as it goes
-  if (s.any_signal) signal_tile<T, VX, SHIFT>(p, s, nx, ny, nz);
+  const bool needz = p.zwrap && bz == nz - 1;
+  if (needy || (needx && needz))
+    march_body<T, VX, 1, SHIFT, 15>(p, bx, by, bz, waits);
+  else if (needx)
+    march_body<T, VX, 1, SHIFT, 3>(p, bx, by, bz, waits);
+  else if (needz)
+    march_body<T, VX, 1, SHIFT, 9>(p, bx, by, bz, waits);
+  else
+    march_body<T, VX, 1, SHIFT, 1>(p, bx, by, bz, waits);
+  if (EDGE >= 2) finish_tile<T, VX, SHIFT>(p, s, nx, ny, nz);
 }
 
-// After the march of a boundary CTA whose neighbour is another rank: publish the iteration number in the neighbour's mailbox
-// word for this tile.  Everything is derived again from the block index (read through an opaque asm, so that the
-// compiler does not keep tile coordinates and face masks alive across the marching loop).  Only warp 0 stays: the others
-// arrive at a named barrier and exit -- a CTA's registers return to the SM when its LAST warp exits, and the fence below
-// waits for an NVLink round trip.
-template <typename T, int VX, bool SHIFT> __device__ __noinline__ void signal_tile(const JacobiParams &p, const FusedSync &s, int nx, int ny, int nz) {
-  int b;
+// After the march of a boundary CTA: ship what the loop could not, then tell the neighbours.  Everything is derived again
+// from the block and thread indices (read through an opaque asm, so that the compiler keeps no tile coordinates, masks or
+// face pointers alive across the marching loop -- with them the 64-register loop spilled and reloaded constants).
+//  x faces: the column parked in shared memory, one plane per lane: a 256-byte line of the dense array per row and chunk.
+//  z faces: this lane's own stores of the first / last plane of the chunk, read back (one load per lane; the z-face CTAs
+//           are 1 in 8 and, with the rotated z order, not the last ones of the grid).
+//  y faces the loop could not serve (y_store_in_loop): copied from this lane's own stores, plane by plane.
+//  Signalling: only warp 0 stays -- the others arrive at a named barrier and exit (a CTA's registers return to the SM when
+//  its LAST warp exits, and the release below waits for an NVLink round trip).
+template <typename T, int VX, bool SHIFT> __device__ __noinline__ void finish_tile(const JacobiParams &p, const FusedSync &s, int nx, int ny, int nz) {
+  using V = Vec<T, VX>;
+  int b, tid;
   asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(b));
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
   const int bx = b % nx;
   b /= nx;
   const int by = b % ny;
   int bz = b / ny + s.zrot;
   if (bz >= nz) bz -= nz;
+  const int lane = tid & 31, warp = tid >> 5;
+  const long long S = p.slice, P = p.pitch, es = (long long)sizeof(T);
+  const int y = p.lo[1] + by * 8 + warp;
+  const int shift = SHIFT ? (int)((((unsigned long long)y * (unsigned long long)P) & (sizeof(T) * VX - 1)) / sizeof(T)) : 0;
+  const int x0w = p.x0a + bx * 32 * VX - shift;
+  const int x = x0w + lane * VX;
+  const int z0 = p.lo[2] + bz * p.zchunk;
+  const int z1 = min(z0 + p.zchunk, p.hi[2]);
+  if (y < p.hi[1] && x0w < p.hi[0]) { // warp-uniform: this warp marched
+    const bool full = (x >= p.lo[0]) && (x + VX <= p.hi[0]);
+    unsigned cell_ok = 0;
+    int xside = -1;
+#pragma unroll
+    for (int i = 0; i < VX; ++i) {
+      if (x + i >= p.lo[0] && x + i < p.hi[0]) cell_ok |= 1u << i;
+      if (x + i == p.lo[0] && p.push_ptr[0]) xside = 0;
+      if (x + i == p.hi[0] - 1 && p.push_ptr[1]) xside = 1;
+    }
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      if (!__ballot_sync(0xffffffffu, xside == side)) continue; // warp-uniform
+      __syncwarp();
+      if (lane < z1 - z0) {
+        char *t = p.xdense[side] ? p.push_ptr[side] + (long long)y * p.push_pitch[side] + (long long)(z0 + lane) * es
+                                 : p.push_ptr[side] + (long long)(z0 + lane) * p.push_slice[side] + (long long)y * p.push_pitch[side];
+        *reinterpret_cast<T *>(t) = xstage_row<T>(side, warp)[lane];
+      }
+    }
+    if (cell_ok) {
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        if (!(side == 0 ? z0 == p.lo[2] : z1 == p.hi[2]) || !p.push_ptr[4 + side]) continue;
+        const int zf = side == 0 ? z0 : z1 - 1;
+        const char *r = p.dst + (long long)zf * S + (long long)y * P + (long long)x * es;
+        char *t = p.push_ptr[4 + side] + (long long)y * p.push_pitch[4 + side] + (long long)x * es;
+        if (full && ((unsigned long long)t % sizeof(V)) == 0) {
+          V v;
+#pragma unroll
+          for (int i = 0; i < VX; ++i) v.v[i] = __ldcg(reinterpret_cast<const T *>(r) + i);
+          *reinterpret_cast<V *>(t) = v;
+        } else {
+#pragma unroll
+          for (int i = 0; i < VX; ++i)
+            if (cell_ok & (1u << i)) reinterpret_cast<T *>(t)[i] = __ldcg(reinterpret_cast<const T *>(r) + i);
+        }
+      }
+    }
+    const int ydir = (y == p.lo[1] && p.push_ptr[2]) ? 2 : ((y == p.hi[1] - 1 && p.push_ptr[3]) ? 3 : -1);
+    if (ydir >= 0) { // warp-uniform
+      const bool ypost = !y_store_in_loop<T, VX>(p, ydir, x, z0, full, cell_ok);
+      // (a one-row subdomain faces both y neighbours: the second side always goes the slow way)
+      const bool ypost_hi = ydir == 2 && y == p.hi[1] - 1 && p.push_ptr[3];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int d = k == 0 ? ydir : 3;
+        if (k == 0 ? !ypost : !ypost_hi) continue;
+        const char *r = p.dst + (long long)y * P + (long long)x * es;
+        char *t = p.push_ptr[d] + (long long)x * es;
+        for (int zz = z0; zz < z1; ++zz) {
+#pragma unroll
+          for (int i = 0; i < VX; ++i)
+            if (cell_ok & (1u << i)) reinterpret_cast<T *>(t + (long long)zz * p.push_slice[d])[i] = __ldcg(reinterpret_cast<const T *>(r + (long long)zz * S) + i);
+        }
+      }
+    }
+  }
+  if (!s.any_signal) return;
   const int nxhi = SHIFT ? min(nx, 2) : 1;
   unsigned faces = 0;
   if (bx == 0 && p.push_ptr[0] && s.signal_row[0]) faces |= 1u;
@@ -486,12 +567,12 @@ template <typename T, int VX, bool SHIFT> __device__ __noinline__ void signal_ti
   if (bz == 0 && p.push_ptr[4] && s.signal_row[4]) faces |= 16u;
   if (bz == nz - 1 && p.push_ptr[5] && s.signal_row[5]) faces |= 32u;
   if (!faces) return; // CTA-uniform
-  if (threadIdx.x >= 32) {
-    asm volatile("bar.arrive 1, 256;" ::: "memory"); // my pushes are issued (ordered before warp 0's fence at CTA scope)
+  if (tid >= 32) {
+    asm volatile("bar.arrive 1, 256;" ::: "memory"); // my pushes are issued (ordered before warp 0's release at CTA scope)
     return;
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     // st.release.sys: every warp's pushes (ordered before this point by the barrier) have landed in the neighbour before
     // the flag does; no separate __threadfence_system() (measured: a second MEMBAR.SYS per boundary CTA)
     const uint32_t value = s.signal_value;
@@ -502,20 +583,14 @@ template <typename T, int VX, bool SHIFT> __device__ __noinline__ void signal_ti
   }
 }
 
-// Variants (SB_FUSED_REGS, SB_FUSED_SPLIT; defaults chosen by measurement, profiles/README.md):
-//   REGS 64 / 56: with 64 registers a CTA's last warp -- lingering in the fences of the arrival / shipping code after the
-//     other seven have exited -- holds registers the next CTA needs (4 x 256 x 64 = the whole file); with 56 a new CTA fits
-//     next to four stragglers, at the price of a spilled loop invariant.
-//   SPLIT: CTAs that touch no face run a second, plain copy of the loop.
-template <typename T, int VX, bool SHIFT, int EDGE, bool SPLIT>
-__global__ void __maxnreg__(56)
-    jacobi_fused_kernel56(const __grid_constant__ JacobiParams p, const __grid_constant__ FusedSync s, int nx, int ny, int nz) {
-  fused_body<T, VX, SHIFT, EDGE, SPLIT>(p, s, nx, ny, nz);
-}
-template <typename T, int VX, bool SHIFT, int EDGE, bool SPLIT>
+// EDGE 1: no face is pushed (every neighbour is this subdomain itself, read in place); 2: pushes, per-tile flags.
+// 64 registers, 4 CTAs per SM.  (Tried: a 56-register build, so that a new CTA fits beside warps lingering in signal_tile
+// -- it spills loop invariants and was 4 % slower at N = 2; one loop for all CTAs instead of the per-tile choice: the
+// inner 64 % pay for the boundary code.)
+template <typename T, int VX, bool SHIFT, int EDGE>
 __global__ void __launch_bounds__(256, 4)
     jacobi_fused_kernel(const __grid_constant__ JacobiParams p, const __grid_constant__ FusedSync s, int nx, int ny, int nz) {
-  fused_body<T, VX, SHIFT, EDGE, SPLIT>(p, s, nx, ny, nz);
+  fused_body<T, VX, SHIFT, EDGE>(p, s, nx, ny, nz);
 }
 
 // One thread per cell: thin regions (the +-x exterior slabs are 1..r cells wide in x).
@@ -660,23 +735,13 @@ template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p
     if (s.wait_row[f]) s.any_wait = 1;
     if (s.signal_row[f]) s.any_signal = 1;
   }
-  const bool regs56 = env_int("SB_FUSED_REGS", 56) == 56;
-  const bool split = env_int("SB_FUSED_SPLIT", 1) != 0;
   const bool dense_ghosts = p.xghost_ptr[0] || p.xghost_ptr[1];
   bool any_push = false;
   for (int f = 0; f < 6; ++f) any_push = any_push || p.push_ptr[f];
-  auto go = [&](auto kern) { kern<<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z); };
-  if (!any_push && !dense_ghosts) { // every face is a periodic self-neighbour read in place (one GPU): no push code in the loop
-    split ? go(jacobi_fused_kernel<T, VX, SHIFT, 1, true>) : go(jacobi_fused_kernel<T, VX, SHIFT, 1, false>);
-    return 1;
-  }
-  if (regs56) {
-    if (dense_ghosts) split ? go(jacobi_fused_kernel56<T, VX, SHIFT, 3, true>) : go(jacobi_fused_kernel56<T, VX, SHIFT, 3, false>);
-    else split ? go(jacobi_fused_kernel56<T, VX, SHIFT, 2, true>) : go(jacobi_fused_kernel56<T, VX, SHIFT, 2, false>);
-  } else {
-    if (dense_ghosts) split ? go(jacobi_fused_kernel<T, VX, SHIFT, 3, true>) : go(jacobi_fused_kernel<T, VX, SHIFT, 3, false>);
-    else split ? go(jacobi_fused_kernel<T, VX, SHIFT, 2, true>) : go(jacobi_fused_kernel<T, VX, SHIFT, 2, false>);
-  }
+  if (!any_push && !dense_ghosts) // every face is a periodic self-neighbour read in place (one GPU)
+    jacobi_fused_kernel<T, VX, SHIFT, 1><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
+  else
+    jacobi_fused_kernel<T, VX, SHIFT, 2><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
   return 1;
 }
 
@@ -837,7 +902,8 @@ int launch_jacobi_fused(const JacobiParams &p_in, const FusedSync &sync_in, int 
   // x wrap (periodic self-neighbour read in place) works through the edge lanes' scalar load, so the first compute cell
   // must open lane 0 of the first strip and the last one must close lane 31 of the last strip; otherwise the ghost
   // column is read by a vector load or a shuffle and the x faces are pushed into the ghost cells like any other face
-  if (p.xwrap && !(!shift && p.x0a == p.lo[0] && (p.hi[0] - p.lo[0]) % (32 * vx) == 0)) p.xwrap = 0;
+  // (phase-shifted FP32 rows: the same conditions; there the ghost element inside a vector is patched, see march_body)
+  if (p.xwrap && !(p.x0a == p.lo[0] && (p.hi[0] - p.lo[0]) % (32 * vx) == 0)) p.xwrap = 0;
   if (p.xwrap) p.push_ptr[0] = p.push_ptr[1] = nullptr;
   if (p.xghost_ptr[0] || p.xghost_ptr[1]) {
     // a dense received x array is read by the edge lanes' scalar load: same layout conditions as the wrap
