@@ -305,6 +305,11 @@ def run_ours(args, rank, world):
     else:
         gpus = [local]
     X, Y, Z = scaled_size(n, n, n, ngpu)
+    cut = os.environ.get("SB_BENCH_CUT", "")  # diagnostics: which axis the weak-scaling rule grows first (default x, as the reference)
+    if cut == "y":
+        X, Y, Z = Z, X, Y
+    elif cut == "z":
+        X, Y, Z = Y, Z, X
 
     dd = sb.DistributedDomain(X, Y, Z)
     dd.set_gpus(gpus)

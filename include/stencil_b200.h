@@ -184,16 +184,21 @@ int sb_jacobi3d_fused(sb_pitched dst, sb_pitched src, int dtype_size, const int6
 /* The same launch with the ordering BETWEEN RANKS inside the kernel, replacing the reference's per-iteration host
  * synchronisation (DistributedDomain::exchange() returns after MPI_Waitall / stream syncs, src/stencil.cu:1120-1186;
  * bin/jacobi3d.cu:337-365) and this library's own sb_wait / sb_signal launches.
- * Every boundary tile of the kernel (256 threads: one 32-lane strip x 8 rows x one z chunk of 32 planes) ships its own face
- * cells into the neighbour after its march, fences at system scope and
- * writes signal_value into signal_rows[f][tile] -- a uint32 array of SB_FUSED_MAX_GROUPS words in the NEIGHBOUR's memory
- * (peer / IPC mapped): its mailbox row for the face it shares with this subdomain.  Before marching, a CTA on face f polls
- * wait_rows[f][tile] (this GPU's own mailbox row for face f, written by the neighbour across f; relaxed loads + one fence) until
- * (int32)(word - wait_value) >= 0.  Protocol: iteration e waits for e and signals e + 1 -- a neighbour that has shipped
- * tile t of iteration e - 1 has (a) filled the ghost cells iteration e reads there and (b) stopped reading the ghost cells
- * iteration e overwrites there.  Neighbours walk their grids in the same order, so in steady state every word was written
- * an iteration earlier and nobody spins.  Faces: -x,+x,-y,+y,-z,+z.  NULL rows: no wait / no signal on that face
- * (neighbour in the same process: order the launches with stream events).  sync == NULL: no handshake at all. */
+ * Every boundary tile of the kernel (256 threads: one 32-lane strip x 8 rows x one z chunk of 32 planes) parks its face
+ * cells in shared memory while it marches and stores them into the neighbour when it is done; there is no fence and no
+ * flag per tile.  Instead the FIRST CTA of the launch writes signal_value (release, system scope) into signal_rows[f][0]
+ * for every face f with a row -- a uint32 word in the NEIGHBOUR's memory (peer / IPC mapped): its mailbox for the face it
+ * shares with this subdomain.  The kernel boundary has completed every store of the previous launch on this stream, so
+ * the word says "my previous iteration is complete, pushes and reads".  Before marching, a CTA on face f polls
+ * wait_rows[f][0] (this GPU's own mailbox for face f, written by the neighbour across f; ld.acquire.sys) until
+ * (int32)(word - wait_value) >= 0.  Protocol: the launch of iteration e carries wait_value = signal_value = e -- a
+ * neighbour that has STARTED iteration e has (a) filled the ghost cells iteration e reads here and (b) stopped reading
+ * the ghost cells iteration e overwrites there.  Tiles that touch no face never wait.  (Round-2 measurements, 8 ranks:
+ * one release per boundary tile cost 19 us per iteration -- the releasing warp lingers for an NVLink round trip and
+ * keeps its CTA slot -- against a skew of a few microseconds between the ranks' kernel starts.)
+ * Faces: -x,+x,-y,+y,-z,+z.  NULL rows: no wait / no signal on that face (neighbour in the same process: order the
+ * launches with stream events).  sync == NULL: no handshake at all.  The rows keep SB_FUSED_MAX_GROUPS words (the
+ * per-tile protocol's size); only word 0 is used. */
 #define SB_FUSED_MAX_GROUPS 4096
 typedef struct {
   const uint32_t *wait_rows[6];

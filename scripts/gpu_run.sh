@@ -64,6 +64,17 @@ for stage in "$@"; do
   bench_diag2)
     SB_DEBUG_FUSED=3 bench nowait_nosignal --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
     SB_DEBUG_NOPUSH=1 bench nopush --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity ;;
+  bench_cuts) # which face direction costs what between ranks (2 ranks: one cut along y, then z)
+    for c in y z; do
+      SB_BENCH_CUT=$c bench "cut${c}" --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
+      SB_BENCH_CUT=$c SB_DEBUG_FUSED=3 bench "cut${c}_nowait_nosignal" --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
+      SB_BENCH_CUT=$c SB_DEBUG_NOPUSH=1 bench "cut${c}_nopush" --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
+    done ;;
+  bench_sig) # what a signal costs: the real release, a flag without fence, a 2.5 us sleep without fence (2 ranks, cut along y)
+    for v in 0 4 8; do
+      SB_BENCH_CUT=y SB_DEBUG_FUSED=$v bench "sig$v" --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
+    done
+    SB_DEBUG_FUSED=4 bench "sig4_xcut" --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity ;;
   time_fused) # kernel variants + single-GPU stand-ins for the multi-rank kernels, one box
     timeout 900 python scripts/time_fused.py 512 30 2>&1 | tail -24 | tee "$F/time_fused.txt" ;;
   ncu_fused2) # the fused kernel of the 2-subdomain stand-in (half of its CTAs are boundary CTAs) under ncu

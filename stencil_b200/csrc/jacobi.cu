@@ -63,16 +63,10 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // x-face cells of a boundary tile, parked while it marches (fused kernel): [side][warp = row][plane of the chunk]
 __shared__ unsigned long long g_xstage[2 * 8 * 32];
 template <typename T> __device__ __forceinline__ T *xstage_row(int side, int warp) { return reinterpret_cast<T *>(g_xstage) + (side * 8 + warp) * 32; }
-
-// May the warp owning a y-face row store it into the neighbour from inside the loop?  Only if every lane can store its
-// whole vector, aligned, and the neighbour's planes are as far apart as ours; anything else (odd sizes, phase-shifted FP32
-// rows) is copied after the march from the warp's own stores.  (Asked before the march and again after it.)
-template <typename T, int VX>
-__device__ __forceinline__ bool y_store_in_loop(const JacobiParams &p, int ydir, int x, int z0, bool full, unsigned cell_ok) {
-  const unsigned long long t = (unsigned long long)(p.push_ptr[ydir] + (long long)x * (long long)sizeof(T) + (long long)z0 * p.slice);
-  const bool ok = p.push_slice[ydir] == p.slice && (t % (sizeof(T) * VX)) == 0 && (full || !cell_ok);
-  return __all_sync(0xffffffffu, ok);
-}
+// ... and the y-face row of a boundary tile (512 bytes per plane: 32 lanes x one 16-byte vector), all planes of the chunk
+__shared__ uint4 g_ystage[32 * 32];
+// ... and its z-face plane (8 rows x 512 bytes).  A tile on both z faces (a subdomain of one chunk) parks the -z plane.
+__shared__ uint4 g_zstage[8 * 32];
 
 // Register-blocked z-march (see the file header).  Everything that does not change along z is hoisted
 // out of the loop -- clamped row offsets, store masks, the (y - cy)^2 term of the sphere test -- so a
@@ -88,14 +82,16 @@ __device__ __forceinline__ bool y_store_in_loop(const JacobiParams &p, int ydir,
 //
 // Boundary variants (RY = 1; the boundary CTAs of the fused kernel), MODE bits:
 //   1 EDGE   the cells just outside the subdomain may come from somewhere else -- a periodic self-neighbour is read in place
-//            from the opposite face of src (pointer set-up before the loop; along z the last step of the top chunk is taken
-//            out of the loop) -- and the z faces of the tile are copied to the neighbour after the march.  The loop itself is
-//            the plain one.
+//            from the opposite face of src (pointer set-up before the loop).  The loop itself is the plain one.
 //   2 XPUSH  the x neighbour of the first / last column may come from a dense received array, and the tile's own x-face
 //            cells are parked in shared memory as the march goes (one predicated STS per step).
-//   4 YPUSH  the warp that owns a y-face row stores it a second time, into the neighbour (one predicated STG per step).
-//   8 ZWRAP  a tile of the top chunk whose +z neighbour is the subdomain itself: pc jumps down to the bottom plane before
-//            the last step (one test per step).
+//   4 YPUSH  the warp that owns a y-face row parks it in shared memory as well (one predicated STS.128 per step).  Not a
+//            store into the neighbour: measured, a warp that issues one NVLink store per step runs at NVLink latency
+//            (the y-face CTAs, 3 % of the grid, cost 10 us per iteration that way).
+// z faces cost the loop nothing: the first plane of the bottom chunk and the last plane of the top chunk are computed by
+// two steps taken out of the loop (the top one FIRST, from three planes loaded for it alone -- 2 planes in 32 read twice by
+// 1 CTA in 16), which store their result a second time, into the neighbour, and which know about a periodic
+// self-neighbour along z (the plane beyond the top is the bottom plane).
 // The kernel is latency- and issue-bound at once (53 % issue utilisation with 8 warps per scheduler): every instruction
 // added to the loop shows in the run time, so each boundary CTA runs the leanest variant that serves its faces.
 template <typename T, int VX, int RY, bool SHIFT, int MODE>
@@ -106,7 +102,6 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   constexpr bool EDGE = (MODE & 1) != 0; // EDGE
   constexpr bool XP = (MODE & 2) != 0;
   constexpr bool YP = (MODE & 4) != 0;
-  constexpr bool ZW = (MODE & 8) != 0;
   using V = Vec<T, VX>;
   constexpr int WY = 8; // warps stacked in y
   const int lane = threadIdx.x & 31;
@@ -138,7 +133,7 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   const char *ph[RY]; // edge scalar of each row, plane z
   char *pw[RY];       // output rows, plane z
   const bool edge_lane = (lane == 0) || (lane == 31);
-  long long phstep = S; // per-plane advance of ph (mode 3: a dense x-ghost array is z fastest)
+  long long phstep = S; // per-plane advance of ph (XPUSH: a dense x-ghost array is z fastest)
   int hxv = lane == 0 ? x - 1 : x + VX;
   if (EDGE && p.xwrap) { // periodic self-neighbour: the cell beyond a face is the first / last cell of the same row
     if (hxv == p.lo[0] - 1) hxv = p.hi[0] - 1;
@@ -187,6 +182,7 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
         if (wrap_i == i) v.v[i] = w;
     }
   };
+  const long long zspan = (long long)(p.hi[2] - p.lo[2]) * S; // a periodic self-neighbour along z is this many bytes away
 
   // store masks
   bool row_ok[RY];
@@ -218,8 +214,7 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   //  Everything that happens after the march is in finish_tile, which derives its own indices: nothing of it is live here.
   int xsi = -1;       // which element of this lane's vector is an x-face cell (-1: none; a lane never holds both faces: ex >= 16)
   T *xsp = nullptr;   // where that cell of the current plane is parked
-  long long ydiff = 0;
-  bool ypush = false;
+  uint4 *ysp = nullptr; // YPUSH: where this lane's vector of the current plane is parked (null: not a y-face row)
   if (XP && row_ok[0]) {
 #pragma unroll
     for (int i = 0; i < VX; ++i) {
@@ -227,39 +222,30 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
       if (x + i == p.hi[0] - 1 && p.push_ptr[1]) xsi = i, xsp = xstage_row<T>(1, warp);
     }
   }
-  if (YP && row_ok[0]) {
-    const int ydir = (y == p.lo[1] && p.push_ptr[2]) ? 2 : ((y == p.hi[1] - 1 && p.push_ptr[3]) ? 3 : -1);
-    if (ydir >= 0) {
-      ydiff = (p.push_ptr[ydir] + (long long)x * (long long)sizeof(T) + (long long)z0 * S) - pw[0];
-      ypush = y_store_in_loop<T, VX>(p, ydir, x, z0, full, cell_ok);
-    }
+  if (YP && sizeof(V) == 16 && row_ok[0]) {
+    // (a tile on both y faces -- a subdomain of at most 8 rows -- parks the -y row; finish_tile copies the other one)
+    if ((y == p.lo[1] && p.push_ptr[2]) || (y == p.hi[1] - 1 && p.push_ptr[3] && !(by == 0 && p.push_ptr[2]))) ysp = g_ystage + lane;
   }
 
   // boundary CTAs of the fused kernel: the flag poll issued before all this set-up must have completed before any load
   if (wait_barrier) __syncthreads();
   V A[RY], B[RY], C[RY];
-#pragma unroll
-  for (int j = 0; j < RY; ++j) {
-    // plane z0-1 (a periodic self-neighbour along z: the ghost plane below the subdomain is its own top plane, read in place)
-    const char *pa = pc[j] - 2 * S;
-    if (EDGE && p.zwrap && z0 == p.lo[2]) pa += (long long)(p.hi[2] - p.lo[2]) * S;
-    A[j] = *reinterpret_cast<const V *>(pa);
-    B[j] = *reinterpret_cast<const V *>(pc[j] - S); // plane z0
-    patch(A[j], (EDGE && p.zwrap && z0 == p.lo[2]) ? 2 - (long long)(p.hi[2] - p.lo[2]) : 2);
-    patch(B[j], 1);
-  }
-  // ... and the plane above the top one is the bottom plane: pc jumps down before the last step of the top chunk (ZWRAP:
-  // only the CTAs of the top chunk carry the test)
-  const int zjump = (ZW && p.zwrap && z1 == p.hi[2]) ? p.hi[2] - 1 : -1;
-  if (ZW && zjump == z0) {
-#pragma unroll
-    for (int j = 0; j < RY; ++j) pc[j] -= (long long)(p.hi[2] - p.lo[2]) * S;
-    if (SHIFT) wrap_p -= (long long)(p.hi[2] - p.lo[2]) * S;
-  }
   const int zlast = p.raw[2] - 1; // last plane that may be touched (prefetch guard)
   int z = z0;
+  // XPUSH: the x neighbour of the first / last compute cell may come from a dense received array [y][z] (z fastest), which
+  // is not part of the rows the march prefetches: a load per step put an L2 miss on every fourth step's critical path
+  // (measured: 15 us per iteration with a quarter of the tiles on x faces).  The chunk's 256-byte line of this row is
+  // pulled into L1 here, one plane per lane; the edge lane's loads then hit.
+  if (XP) {
+    const int gside = (x0w == p.lo[0] && p.xghost_ptr[0]) ? 0 : ((x0w + 32 * VX == p.hi[0] && p.xghost_ptr[1]) ? 1 : -1);
+    if (gside >= 0 && lane < z1 - z0)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.xghost_ptr[gside] + (long long)y * p.xghost_pitch[gside] + (long long)(z0 + lane) * (long long)sizeof(T)));
+  }
 
-  auto step = [&](const V(&prev)[RY], const V(&cur)[RY], V(&nxt)[RY]) {
+  // one plane: load z+1, compute z from (z-1, z, z+1), store, advance every running pointer.  ZP (the two steps outside the
+  // loop): also store the result into the z neighbours named by zmask (bit 0: -z, bit 1: +z).
+  auto step = [&](auto zp_tag, const unsigned zmask, const V(&prev)[RY], const V(&cur)[RY], V(&nxt)[RY]) {
+    constexpr bool ZP = decltype(zp_tag)::value;
 #pragma unroll
     for (int j = 0; j < RY; ++j) nxt[j] = *reinterpret_cast<const V *>(pc[j]);
     if (EDGE && SHIFT) {
@@ -334,7 +320,11 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
           if (xsi == i) v = out.v[i];
         *xsp++ = v;
       }
-      if (YP && ypush && full) *reinterpret_cast<V *>(pw[j] + ydiff) = out;
+      if (YP && ysp) {
+        *reinterpret_cast<V *>(ysp) = out;
+        ysp += 32;
+      }
+      if (ZP && sizeof(V) == 16 && zmask) *reinterpret_cast<V *>(g_zstage + warp * 32 + lane) = out; // leaves in finish_tile
       pc[j] += S;
       ph[j] += XP ? phstep : S;
       pw[j] += S;
@@ -342,19 +332,76 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
     pu += S;
     pd += S;
     ++z;
-    if (ZW && z == zjump) {
-#pragma unroll
-      for (int j = 0; j < RY; ++j) pc[j] -= (long long)(p.hi[2] - p.lo[2]) * S;
-      if (SHIFT) wrap_p -= (long long)(p.hi[2] - p.lo[2]) * S;
-    }
   };
+  using NoZ = std::integral_constant<bool, false>;
+  using WithZ = std::integral_constant<bool, true>;
 
-  while (z < z1) {
-    step(A, B, C);
-    if (z >= z1) break;
-    step(B, C, A);
-    if (z >= z1) break;
-    step(C, A, B);
+  // the last plane of the top chunk first (EDGE): its +z neighbour plane may be the bottom plane (zwrap), and its result
+  // may have to go to the +z neighbour -- neither is the loop's business.  Every running pointer moves up, the step runs,
+  // and they all come back.
+  int zend = z1;
+  if (EDGE && z1 == p.hi[2] && (p.zwrap || p.push_ptr[5])) {
+    const int up = z1 - 1 - z0;
+    const long long d = (long long)up * S;
+#pragma unroll
+    for (int j = 0; j < RY; ++j) pc[j] += d, ph[j] += (long long)up * (XP ? phstep : S), pw[j] += d;
+    pu += d, pd += d, z += up;
+    if (XP) xsp += up;
+    if (YP && ysp) ysp += 32 * up;
+    if (SHIFT) wrap_p += d;
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      const char *pa = pc[j] - 2 * S;
+      const bool below = p.zwrap && up == 0 && z0 == p.lo[2]; // a one-plane subdomain chunk: its own plane, twice
+      if (below) pa += zspan;
+      A[j] = *reinterpret_cast<const V *>(pa);
+      B[j] = *reinterpret_cast<const V *>(pc[j] - S);
+      patch(A[j], below ? 2 - (long long)(p.hi[2] - p.lo[2]) : 2);
+      patch(B[j], 1);
+      if (p.zwrap) pc[j] -= zspan;
+    }
+    if (SHIFT && p.zwrap) wrap_p -= zspan;
+    const unsigned zmask = (p.push_ptr[5] && !(z0 == p.lo[2] && p.push_ptr[4])) ? 2u : 0u; // (on both z faces: finish_tile copies)
+    step(WithZ{}, zmask, A, B, C);
+    const long long back = (long long)(up + 1) * S;
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      pc[j] -= back, ph[j] -= (long long)(up + 1) * (XP ? phstep : S), pw[j] -= back;
+      if (p.zwrap) pc[j] += zspan;
+    }
+    pu -= back, pd -= back, z -= up + 1;
+    if (XP) xsp -= up + 1;
+    if (YP && ysp) ysp -= 32 * (up + 1);
+    if (SHIFT) {
+      wrap_p -= back;
+      if (p.zwrap) wrap_p += zspan;
+    }
+    zend = z1 - 1;
+  }
+  if (z < zend) {
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      // plane z0-1 (a periodic self-neighbour along z: the ghost plane below the subdomain is its own top plane, read in place)
+      const char *pa = pc[j] - 2 * S;
+      const bool below = EDGE && p.zwrap && z0 == p.lo[2];
+      if (below) pa += zspan;
+      A[j] = *reinterpret_cast<const V *>(pa);
+      B[j] = *reinterpret_cast<const V *>(pc[j] - S); // plane z0
+      patch(A[j], below ? 2 - (long long)(p.hi[2] - p.lo[2]) : 2);
+      patch(B[j], 1);
+    }
+    if (EDGE && z0 == p.lo[2] && p.push_ptr[4] && !(z1 == p.hi[2] && p.push_ptr[5])) { // the first plane of the bottom chunk is parked for the -z neighbour
+      step(WithZ{}, 1u, A, B, C);
+#pragma unroll
+      for (int j = 0; j < RY; ++j) A[j] = B[j], B[j] = C[j];
+    }
+  }
+  while (z < zend) {
+    step(NoZ{}, 0u, A, B, C);
+    if (z >= zend) break;
+    step(NoZ{}, 0u, B, C, A);
+    if (z >= zend) break;
+    step(NoZ{}, 0u, C, A, B);
   }
 }
 
@@ -394,21 +441,21 @@ __global__ void __launch_bounds__(256, MB) jacobi_march_kernel(const __grid_cons
 //    SM's whole L1 (CCTL.IVALL), which costs the co-resident CTAs an L2 round trip, so there is exactly one per face.
 constexpr int kMaxGroups = SB_FUSED_MAX_GROUPS;
 
-// mailbox word of the tile (bx, by, bz) on face f: the same arithmetic on both sides of the face (neighbours across a
-// face have equal extents on the other two axes, hence equal tile counts there)
-__device__ __forceinline__ int tile_slot(int f, int bx, int by, int bz, int nx, int ny) {
-  return f < 2 ? bz * ny + by : (f < 4 ? bz * nx + bx : by * nx + bx);
-}
-
 template <typename T, int VX, bool SHIFT> __device__ __noinline__ void finish_tile(const JacobiParams &p, const FusedSync &s, int nx, int ny, int nz);
 
 template <typename T, int VX, bool SHIFT, int EDGE>
 __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSync &s, int nx, int ny, int nz) {
   int b = blockIdx.x;
-  const int bx = b % nx;
+  // The first CTA of iteration e tells every neighbour rank "my iteration e - 1 is complete" (the kernel boundary has
+  // made all its stores visible; nothing of this kernel is outstanding yet, so the release costs nothing).
+  if (EDGE >= 2 && s.any_signal && b == 0 && threadIdx.x < 6 && s.signal_row[threadIdx.x])
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.signal_row[threadIdx.x]), "r"(s.signal_value) : "memory");
+  int bx = b % nx + s.xrot;
   b /= nx;
-  const int by = b % ny;
+  int by = b % ny + s.yrot;
   int bz = b / ny + s.zrot;
+  if (bx >= nx) bx -= nx;
+  if (by >= ny) by -= ny;
   if (bz >= nz) bz -= nz;
   // the faces this CTA's cells lie on (phase-shifted rows end one strip later than the others, so with SHIFT the last TWO
   // strips along x may hold cells of the +x face)
@@ -450,23 +497,14 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
       }
     };
 #pragma unroll
-    for (int f = 0; f < 6; ++f) {
-      if (!(faces >> f & 1u) || !s.wait_row[f]) continue;
-      poll(s.wait_row[f] + tile_slot(f, bx, by, bz, nx, ny));
-      if (SHIFT && (f == 2 || f == 3)) { // strips of rows of different phase overlap their neighbours by VX / 2 cells
-        if (bx > 0) poll(s.wait_row[f] + tile_slot(f, bx - 1, by, bz, nx, ny));
-        if (bx + 1 < nx) poll(s.wait_row[f] + tile_slot(f, bx + 1, by, bz, nx, ny));
-      }
-    }
+    for (int f = 0; f < 6; ++f)
+      if ((faces >> f & 1u) && s.wait_row[f]) poll(s.wait_row[f]);
   }
 
-  const bool needz = p.zwrap && bz == nz - 1;
-  if (needy || (needx && needz))
-    march_body<T, VX, 1, SHIFT, 15>(p, bx, by, bz, waits);
+  if (needy)
+    march_body<T, VX, 1, SHIFT, 7>(p, bx, by, bz, waits);
   else if (needx)
     march_body<T, VX, 1, SHIFT, 3>(p, bx, by, bz, waits);
-  else if (needz)
-    march_body<T, VX, 1, SHIFT, 9>(p, bx, by, bz, waits);
   else
     march_body<T, VX, 1, SHIFT, 1>(p, bx, by, bz, waits);
   if (EDGE >= 2) finish_tile<T, VX, SHIFT>(p, s, nx, ny, nz);
@@ -476,8 +514,7 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
 // from the block and thread indices (read through an opaque asm, so that the compiler keeps no tile coordinates, masks or
 // face pointers alive across the marching loop -- with them the 64-register loop spilled and reloaded constants).
 //  x faces: the column parked in shared memory, one plane per lane: a 256-byte line of the dense array per row and chunk.
-//  z faces: this lane's own stores of the first / last plane of the chunk, read back (one load per lane; the z-face CTAs
-//           are 1 in 8 and, with the rotated z order, not the last ones of the grid).
+//  (z faces went out from the registers of the two steps taken out of the loop, see march_body.)
 //  y faces the loop could not serve (y_store_in_loop): copied from this lane's own stores, plane by plane.
 //  Signalling: only warp 0 stays -- the others arrive at a named barrier and exit (a CTA's registers return to the SM when
 //  its LAST warp exits, and the release below waits for an NVLink round trip).
@@ -486,10 +523,12 @@ template <typename T, int VX, bool SHIFT> __device__ __noinline__ void finish_ti
   int b, tid;
   asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(b));
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-  const int bx = b % nx;
+  int bx = b % nx + s.xrot;
   b /= nx;
-  const int by = b % ny;
+  int by = b % ny + s.yrot;
   int bz = b / ny + s.zrot;
+  if (bx >= nx) bx -= nx;
+  if (by >= ny) by -= ny;
   if (bz >= nz) bz -= nz;
   const int lane = tid & 31, warp = tid >> 5;
   const long long S = p.slice, P = p.pitch, es = (long long)sizeof(T);
@@ -519,67 +558,85 @@ template <typename T, int VX, bool SHIFT> __device__ __noinline__ void finish_ti
         *reinterpret_cast<T *>(t) = xstage_row<T>(side, warp)[lane];
       }
     }
-    if (cell_ok) {
+    // z faces: the plane this very thread parked; a tile on both z faces (or one marching narrow vectors) reads its own
+    // stores back instead
+    const bool zlo = z0 == p.lo[2] && p.push_ptr[4], zhi = z1 == p.hi[2] && p.push_ptr[5];
+    if ((zlo || zhi) && cell_ok) {
+      const bool parked = sizeof(V) == 16 && !(zlo && zhi);
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
-        if (!(side == 0 ? z0 == p.lo[2] : z1 == p.hi[2]) || !p.push_ptr[4 + side]) continue;
-        const int zf = side == 0 ? z0 : z1 - 1;
-        const char *r = p.dst + (long long)zf * S + (long long)y * P + (long long)x * es;
+        if (!(side == 0 ? zlo : zhi)) continue;
         char *t = p.push_ptr[4 + side] + (long long)y * p.push_pitch[4 + side] + (long long)x * es;
-        if (full && ((unsigned long long)t % sizeof(V)) == 0) {
-          V v;
+        V v;
+        if (parked) {
+          v = *reinterpret_cast<const V *>(g_zstage + warp * 32 + lane);
+        } else {
+          const char *r = p.dst + (long long)(side == 0 ? z0 : z1 - 1) * S + (long long)y * P + (long long)x * es;
 #pragma unroll
-          for (int i = 0; i < VX; ++i) v.v[i] = __ldcg(reinterpret_cast<const T *>(r) + i);
+          for (int i = 0; i < VX; ++i) v.v[i] = (cell_ok & (1u << i)) ? __ldcg(reinterpret_cast<const T *>(r) + i) : T(0);
+        }
+        if (full && ((unsigned long long)t % sizeof(V)) == 0) {
           *reinterpret_cast<V *>(t) = v;
         } else {
 #pragma unroll
           for (int i = 0; i < VX; ++i)
-            if (cell_ok & (1u << i)) reinterpret_cast<T *>(t)[i] = __ldcg(reinterpret_cast<const T *>(r) + i);
-        }
-      }
-    }
-    const int ydir = (y == p.lo[1] && p.push_ptr[2]) ? 2 : ((y == p.hi[1] - 1 && p.push_ptr[3]) ? 3 : -1);
-    if (ydir >= 0) { // warp-uniform
-      const bool ypost = !y_store_in_loop<T, VX>(p, ydir, x, z0, full, cell_ok);
-      // (a one-row subdomain faces both y neighbours: the second side always goes the slow way)
-      const bool ypost_hi = ydir == 2 && y == p.hi[1] - 1 && p.push_ptr[3];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int d = k == 0 ? ydir : 3;
-        if (k == 0 ? !ypost : !ypost_hi) continue;
-        const char *r = p.dst + (long long)y * P + (long long)x * es;
-        char *t = p.push_ptr[d] + (long long)x * es;
-        for (int zz = z0; zz < z1; ++zz) {
-#pragma unroll
-          for (int i = 0; i < VX; ++i)
-            if (cell_ok & (1u << i)) reinterpret_cast<T *>(t + (long long)zz * p.push_slice[d])[i] = __ldcg(reinterpret_cast<const T *>(r + (long long)zz * S) + i);
+            if (cell_ok & (1u << i)) reinterpret_cast<T *>(t)[i] = v.v[i];
         }
       }
     }
   }
-  if (!s.any_signal) return;
-  const int nxhi = SHIFT ? min(nx, 2) : 1;
-  unsigned faces = 0;
-  if (bx == 0 && p.push_ptr[0] && s.signal_row[0]) faces |= 1u;
-  if (bx >= nx - nxhi && p.push_ptr[1] && s.signal_row[1]) faces |= 2u;
-  if (by == 0 && p.push_ptr[2] && s.signal_row[2]) faces |= 4u;
-  if (by == ny - 1 && p.push_ptr[3] && s.signal_row[3]) faces |= 8u;
-  if (bz == 0 && p.push_ptr[4] && s.signal_row[4]) faces |= 16u;
-  if (bz == nz - 1 && p.push_ptr[5] && s.signal_row[5]) faces |= 32u;
-  if (!faces) return; // CTA-uniform
-  if (tid >= 32) {
-    asm volatile("bar.arrive 1, 256;" ::: "memory"); // my pushes are issued (ordered before warp 0's release at CTA scope)
-    return;
-  }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  if (tid == 0) {
-    // st.release.sys: every warp's pushes (ordered before this point by the barrier) have landed in the neighbour before
-    // the flag does; no separate __threadfence_system() (measured: a second MEMBAR.SYS per boundary CTA)
-    const uint32_t value = s.signal_value;
+  // y faces: the parked row leaves with every warp taking its share of the planes (stores into the neighbour are slow one
+  // after the other, not side by side); vectors narrower than 16 bytes and the second row of a tile on both y faces are
+  // copied from the tile's own stores instead
+  {
+    const int ylo = (by == 0 && p.push_ptr[2]) ? 1 : 0, yhi = (by == ny - 1 && p.push_ptr[3]) ? 1 : 0; // CTA-uniform
+    if (ylo | yhi) {
+      const int ydir = ylo ? 2 : 3;
+      const int yrow = ylo ? p.lo[1] : p.hi[1] - 1;
+      // the owner row's strip (its phase decides where the lanes' vectors start)
+      const int rshift = SHIFT ? (int)((((unsigned long long)yrow * (unsigned long long)P) & (sizeof(T) * VX - 1)) / sizeof(T)) : 0;
+      const int rx0 = p.x0a + bx * 32 * VX - rshift;
+      const int rx = rx0 + lane * VX;
+      unsigned rcell = 0;
 #pragma unroll
-    for (int f = 0; f < 6; ++f)
-      if (faces >> f & 1u)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.signal_row[f] + tile_slot(f, bx, by, bz, nx, ny)), "r"(value) : "memory");
+      for (int i = 0; i < VX; ++i)
+        if (rx + i >= p.lo[0] && rx + i < p.hi[0]) rcell |= 1u << i;
+      const bool rfull = (rx >= p.lo[0]) && (rx + VX <= p.hi[0]);
+      if (sizeof(V) == 16 && rx0 < p.hi[0]) {
+        __syncthreads(); // every warp's march is over: the parked planes are complete
+        for (int pl = warp; pl < z1 - z0; pl += 8) {
+          const V v = *reinterpret_cast<const V *>(g_ystage + pl * 32 + lane);
+          char *t = p.push_ptr[ydir] + (long long)rx * es + (long long)(z0 + pl) * p.push_slice[ydir];
+          if (rfull && ((unsigned long long)t % sizeof(V)) == 0) {
+            *reinterpret_cast<V *>(t) = v;
+          } else {
+#pragma unroll
+            for (int i = 0; i < VX; ++i)
+              if (rcell & (1u << i)) reinterpret_cast<T *>(t)[i] = v.v[i];
+          }
+        }
+      }
+      // the slow way: this warp's own row, read back plane by plane
+      const bool slow_lo = sizeof(V) != 16 && ylo && y == p.lo[1];
+      const bool slow_hi = yhi && y == p.hi[1] - 1 && (sizeof(V) != 16 || ylo);
+      if ((slow_lo || slow_hi) && y < p.hi[1] && x0w < p.hi[0]) {
+        unsigned cell_ok = 0;
+#pragma unroll
+        for (int i = 0; i < VX; ++i)
+          if (x + i >= p.lo[0] && x + i < p.hi[0]) cell_ok |= 1u << i;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (k == 0 ? !slow_lo : !slow_hi) continue;
+          const char *r = p.dst + (long long)y * P + (long long)x * es;
+          char *t = p.push_ptr[2 + k] + (long long)x * es;
+          for (int zz = z0; zz < z1; ++zz) {
+#pragma unroll
+            for (int i = 0; i < VX; ++i)
+              if (cell_ok & (1u << i)) reinterpret_cast<T *>(t + (long long)zz * p.push_slice[2 + k])[i] = __ldcg(reinterpret_cast<const T *>(r + (long long)zz * S) + i);
+          }
+        }
+      }
+    }
   }
 }
 
@@ -728,8 +785,7 @@ template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p
   const int tiles_y = (ny + 7) / 8;
   if ((long long)tiles_z * tiles_y > kMaxGroups || (long long)tiles_z * tiles_x > kMaxGroups || (long long)tiles_y * tiles_x > kMaxGroups) return -2;
   const long long blocks = (long long)tiles_x * tiles_y * tiles_z;
-  // start in the middle of z when a z face waits for another rank (see the kernel's header)
-  s.zrot = (s.wait_row[4] || s.wait_row[5]) ? tiles_z / 2 : 0;
+  s.xrot = s.yrot = s.zrot = 0;
   s.any_wait = s.any_signal = 0;
   for (int f = 0; f < 6; ++f) {
     if (s.wait_row[f]) s.any_wait = 1;
@@ -738,10 +794,22 @@ template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p
   const bool dense_ghosts = p.xghost_ptr[0] || p.xghost_ptr[1];
   bool any_push = false;
   for (int f = 0; f < 6; ++f) any_push = any_push || p.push_ptr[f];
-  if (!any_push && !dense_ghosts) // every face is a periodic self-neighbour read in place (one GPU)
+  if (!any_push && !dense_ghosts) { // every face is a periodic self-neighbour read in place (one GPU)
     jacobi_fused_kernel<T, VX, SHIFT, 1><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
-  else
+  } else {
+    // Tiles that push stay up to 20 us after their march (8 to 128 stores into the neighbour, a few at a time): the walk
+    // over the grid (x fastest, then y, then z) must not END with them, or the whole kernel ends that much later
+    // (measured at 2 ranks cut along y: 12 us per iteration, with 3 % of the tiles on the faces).  So: the top row of
+    // tiles first, then row 0, 1, ...; the last strip first; and z from the middle, which also keeps the z-face tiles out
+    // of the first wave, where every boundary tile waits for the neighbour rank's kernel to start.
+    static const int rot = env_int("SB_FUSED_ROTATE", 1);
+    if (rot) {
+      s.xrot = tiles_x - 1;
+      s.yrot = tiles_y - 1;
+      s.zrot = tiles_z / 2;
+    }
     jacobi_fused_kernel<T, VX, SHIFT, 2><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
+  }
   return 1;
 }
 

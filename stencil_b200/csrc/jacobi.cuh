@@ -55,7 +55,8 @@ struct FusedSync {
   const uint32_t *wait_row[6];   // per face: this GPU's mailbox row [tile] written by the neighbour across that face (null: no wait)
   uint32_t *signal_row[6];       // per face: the neighbour's mailbox row [tile] for this subdomain (null: neighbour ordered by stream events)
   uint32_t wait_value, signal_value;
-  int zrot, any_wait, any_signal; // set by the launcher
+  int xrot, yrot, zrot;    // set by the launcher: where the walk over the tiles starts on each axis
+  int any_wait, any_signal; // set by the launcher
 };
 
 // Up to 8 thin regions (the exterior slabs of one subdomain) updated by ONE launch.

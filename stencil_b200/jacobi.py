@@ -45,7 +45,7 @@ def fused_x_mode(part, owner, elem_size: int, radius: Radius, mode: str = "") ->
 
     "direct": no x face crosses ranks -- the kernel stores boundary cells into the neighbour's ghost cells (own memory or
               a peer GPU of this process) or reads a periodic self-neighbour in place;
-    "dense":  x faces cross ranks and travel as 256-byte lines into dense receive arrays (kernel mode 3): needs whole warp
+    "dense":  x faces cross ranks and travel as 256-byte lines into dense receive arrays (kernel mode XPUSH): needs whole warp
               strips along x and rows of one 16-byte phase (mode "0" = SB_FUSED_IPC=0 switches it off);
     "queued": fall back to the queued schedule (Jacobi3D.step_async)."""
     from .domain import get_neighbor
@@ -393,8 +393,8 @@ class Jacobi3D:
         self._fused_epoch = 0
         self._ev_fused = None
         self._ghosts_current = False
-        # Ordering between ranks.  One subdomain per rank: inside the kernel -- boundary CTAs poll the mailbox word of
-        # their face group, the CTA that ships a group's slab publishes the iteration number in the neighbour's mailbox
+        # Ordering between ranks.  One subdomain per rank: inside the kernel -- its first CTA publishes the iteration number
+        # in every neighbour's mailbox, boundary CTAs poll the word of the neighbour across their face
         # (sb_jacobi3d_fused_sync); no extra launch.  Several subdomains per rank: one counter per rank, signalled by a tiny
         # kernel after all of them (dist.RemoteDomains.signal_step / wait_step).
         self._sync = None
@@ -460,9 +460,10 @@ class Jacobi3D:
                     if sj != di:
                         s.wait_event(prev[sj])
             sync = self._sync
-            if sync is not None:  # iteration e (of this object: its mailboxes start at zero) waits for e and signals e + 1
-                sync.wait_value = self._fused_epoch & 0xFFFFFFFF
-                sync.signal_value = (self._fused_epoch + 1) & 0xFFFFFFFF
+            if sync is not None:
+                # the kernel of iteration e (of this object: its mailboxes start at zero) publishes e when it starts -- "my
+                # iterations before e are complete" -- and its boundary tiles wait for e from the neighbour across their face
+                sync.wait_value = sync.signal_value = self._fused_epoch & 0xFFFFFFFF
             elif remote is not None:
                 remote.wait_step(remote.step_epoch, s)
             if timing is not None and di == 0:
