@@ -75,6 +75,9 @@ for stage in "$@"; do
       SB_BENCH_CUT=y SB_DEBUG_FUSED=$v bench "sig$v" --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
     done
     SB_DEBUG_FUSED=4 bench "sig4_xcut" --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity ;;
+  bench_rot) # the rotated walk over the tiles, on and off
+    SB_FUSED_ROTATE=0 bench rot0 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
+    SB_FUSED_ROTATE=1 bench rot1 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity ;;
   time_fused) # kernel variants + single-GPU stand-ins for the multi-rank kernels, one box
     timeout 900 python scripts/time_fused.py 512 30 2>&1 | tail -24 | tee "$F/time_fused.txt" ;;
   ncu_fused2) # the fused kernel of the 2-subdomain stand-in (half of its CTAs are boundary CTAs) under ncu

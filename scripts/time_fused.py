@@ -55,6 +55,10 @@ run(1, "plain whole-region kernel (calibration)", fused=False)
 if os.environ.get("SPLITS", "1") == "1":
     # which face direction costs what: two 512^3 subdomains on this GPU, cut along x / y / z (the other two axes wrap in place)
     run(2, "fused, 2 x 512^3 cut along x (dense x lines)", shape=(2 * n, n, n))
+    for dbg, what in ((16, "ghost column instead of the dense array"), (32, "no x parking"), (48, "both")):
+        os.environ["SB_DEBUG_FUSED"] = str(dbg)
+        run(2, "  same, " + what, shape=(2 * n, n, n))
+    del os.environ["SB_DEBUG_FUSED"]
     run(2, "fused, 2 x 512^3 cut along y", shape=(n, 2 * n, n))
     run(2, "fused, 2 x 512^3 cut along z", shape=(n, n, 2 * n))
     run(8, "fused, 8 x 512^3 cut along x, y and z", shape=(2 * n, 2 * n, 2 * n))

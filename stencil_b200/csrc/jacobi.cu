@@ -95,7 +95,7 @@ __shared__ uint4 g_zstage[8 * 32];
 // The kernel is latency- and issue-bound at once (53 % issue utilisation with 8 warps per scheduler): every instruction
 // added to the loop shows in the run time, so each boundary CTA runs the leanest variant that serves its faces.
 template <typename T, int VX, int RY, bool SHIFT, int MODE>
-__device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, const int by, const int bz, const bool wait_barrier = false) {
+__device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, const int by, const int bz, const bool wait_barrier = false, const int debug = 0) {
   static_assert(!SHIFT || (RY == 1 && VX >= 2), "the phase-shifted variant handles one row per warp");
   static_assert(!MODE || RY == 1, "the boundary variants handle one row per warp");
   static_assert(MODE == 0 || (MODE & 1), "XPUSH / YPUSH imply EDGE");
@@ -146,7 +146,7 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
     ph[j] = src + (long long)z0 * S + yo(y + j) + (long long)hx * (long long)sizeof(T);
     if (XP) { // the x neighbour of the first / last compute cell may come from a dense received array [y][z]
       const int side = (lane == 0 && x == p.lo[0]) ? 0 : ((lane == 31 && x + VX == p.hi[0]) ? 1 : -1);
-      if (side >= 0 && p.xghost_ptr[side]) {
+      if (side >= 0 && p.xghost_ptr[side] && !(debug & 16)) {
         ph[j] = p.xghost_ptr[side] + (long long)(y + j) * p.xghost_pitch[side] + (long long)z0 * (long long)sizeof(T);
         phstep = (long long)sizeof(T);
       }
@@ -221,6 +221,7 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
       if (x + i == p.lo[0] && p.push_ptr[0]) xsi = i, xsp = xstage_row<T>(0, warp);
       if (x + i == p.hi[0] - 1 && p.push_ptr[1]) xsi = i, xsp = xstage_row<T>(1, warp);
     }
+    if (debug & 32) xsi = -1;
   }
   if (YP && sizeof(V) == 16 && row_ok[0]) {
     // (a tile on both y faces -- a subdomain of at most 8 rows -- parks the -y row; finish_tile copies the other one)
@@ -417,28 +418,29 @@ __global__ void __launch_bounds__(256, MB) jacobi_march_kernel(const __grid_cons
 // launch_jacobi_fused: the march over the WHOLE compute region of a subdomain, with the halo exchange of the next
 // iteration and the ordering between ranks inside the kernel.
 //
-//  * Blocks run in the natural order (x fastest): measured, gathering the boundary CTAs at the start or the end of the
-//    grid costs 10 % (their 512-byte row segments lose the DRAM locality of whole rows).  CTAs that touch no face of the
-//    subdomain (64 % at 512^3) run the plain loop; boundary CTAs run the EDGE variant, which differs only in where the
-//    cells just outside the subdomain come from.  No push code inside any loop (measured: it cost 36 % more issued
-//    instructions in every boundary CTA).
-//  * Pushing.  A boundary CTA stores its own face cells into the neighbour as it marches (march_body, EDGE): x cells are
-//    parked in shared memory and leave as one 256-byte line per row and chunk, y rows are stored a second time by the warp
-//    that owns them, the +z plane goes out from the registers of the last step.  Nothing is counted, nothing crosses CTAs,
+//  * Tiles are walked x fastest, then y, then z (measured: gathering the boundary tiles at the start or the end of the
+//    grid costs 10 %, their 512-byte row segments lose the DRAM locality of whole rows).  Tiles that touch no face of
+//    the subdomain (64 % at 512^3) run the plain loop; a boundary tile runs the leanest variant of the loop that serves
+//    its faces (march_body MODE).  The kernel is latency- and issue-bound at once: every instruction added to a loop
+//    shows in the run time.
+//  * Pushing.  A boundary tile parks its face cells in shared memory while it marches -- the x column (one STS per step),
+//    the y row (one STS.128 per step of the warp that owns it), the z plane (the two steps taken out of the loop) -- and
+//    stores them into the neighbour when the march is over (finish_tile): x columns as one 256-byte line per row into a
+//    dense array, y rows and z planes as 512-byte rows into the ghost cells.  Stores into the neighbour never sit between
+//    two steps of the march (measured: a warp then runs at NVLink latency), nothing is counted, nothing crosses CTAs,
 //    and no global load follows the march (tried: a copy pass over the finished tile costs microseconds per CTA under a
 //    saturated memory system, and re-reading through a "last CTA of a group" costs an L1 invalidation per fence).
-//  * Signalling.  If the neighbour is another rank, warp 0 -- the other warps exit after arriving at a named barrier --
-//    fences at system scope and publishes the iteration number in the neighbour's mailbox word for this tile
-//    (st.release.sys).  A CTA's registers return to the SM only when its last warp exits, and at 64 registers a new CTA
-//    needs all of them (4 x 256 x 64 = the whole file): the 56-register build lets a new CTA start beside four such
-//    stragglers.
-//  * Waiting.  Before its first load a boundary CTA polls the mailbox words of the tiles across its faces (own memory)
-//    until the neighbour has shipped the previous iteration: that one flag says both "the ghost cells I read are filled"
-//    and "the neighbour's tile is done reading the ghost cells I am about to overwrite".  Neighbours walk their grids in
-//    the same order, so the word was written a whole iteration earlier: x / y tiles by construction, z tiles because the
-//    z order is rotated by half the chunks (s.zrot) -- without the rotation the first chunk of iteration e+1 would need
-//    what the last chunk of iteration e ships.  ONE thread polls (ld.acquire.sys); every acquire also invalidates the
-//    SM's whole L1 (CCTL.IVALL), which costs the co-resident CTAs an L2 round trip, so there is exactly one per face.
+//  * A tile that pushes stays longer (8 to 128 NVLink stores, a few in flight at a time), so the walk is rotated on every
+//    axis: it neither starts nor ends with such tiles (launch_fused).
+//  * Ordering between ranks: ONE release per kernel.  The first CTA of iteration e writes e into every neighbour rank's
+//    mailbox (st.release.sys; the kernel boundary has completed iteration e - 1, pushes and reads alike, and nothing of
+//    this kernel is outstanding yet).  Before its first load a boundary tile polls the word of the neighbour across its
+//    face (own memory, ld.acquire.sys by one thread): "the neighbour has started iteration e" says both "the ghost cells
+//    I read are filled" and "the neighbour is done reading the ghost cells I am about to overwrite".  Inner tiles never
+//    wait.  Tried first: one flag per boundary tile, released by the tile after its pushes -- the releasing warp waits for
+//    an NVLink round trip and keeps its CTA's registers (4 x 256 x 64 = the whole file), 19 us per iteration on 8 ranks;
+//    what the per-kernel flag costs instead is the skew between the ranks' kernel starts, a few microseconds in the
+//    first wave.  Every acquire also invalidates the SM's whole L1 (CCTL.IVALL): exactly one per face and tile.
 constexpr int kMaxGroups = SB_FUSED_MAX_GROUPS;
 
 template <typename T, int VX, bool SHIFT> __device__ __noinline__ void finish_tile(const JacobiParams &p, const FusedSync &s, int nx, int ny, int nz);
@@ -504,7 +506,7 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
   if (needy)
     march_body<T, VX, 1, SHIFT, 7>(p, bx, by, bz, waits);
   else if (needx)
-    march_body<T, VX, 1, SHIFT, 3>(p, bx, by, bz, waits);
+    march_body<T, VX, 1, SHIFT, 3>(p, bx, by, bz, waits, s.debug);
   else
     march_body<T, VX, 1, SHIFT, 1>(p, bx, by, bz, waits);
   if (EDGE >= 2) finish_tile<T, VX, SHIFT>(p, s, nx, ny, nz);
@@ -794,22 +796,22 @@ template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p
   const bool dense_ghosts = p.xghost_ptr[0] || p.xghost_ptr[1];
   bool any_push = false;
   for (int f = 0; f < 6; ++f) any_push = any_push || p.push_ptr[f];
-  if (!any_push && !dense_ghosts) { // every face is a periodic self-neighbour read in place (one GPU)
-    jacobi_fused_kernel<T, VX, SHIFT, 1><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
-  } else {
-    // Tiles that push stay up to 20 us after their march (8 to 128 stores into the neighbour, a few at a time): the walk
-    // over the grid (x fastest, then y, then z) must not END with them, or the whole kernel ends that much later
-    // (measured at 2 ranks cut along y: 12 us per iteration, with 3 % of the tiles on the faces).  So: the top row of
-    // tiles first, then row 0, 1, ...; the last strip first; and z from the middle, which also keeps the z-face tiles out
-    // of the first wave, where every boundary tile waits for the neighbour rank's kernel to start.
-    static const int rot = env_int("SB_FUSED_ROTATE", 1);
-    if (rot) {
-      s.xrot = tiles_x - 1;
-      s.yrot = tiles_y - 1;
-      s.zrot = tiles_z / 2;
-    }
-    jacobi_fused_kernel<T, VX, SHIFT, 2><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
+  // Boundary tiles stay longer than inner ones -- a tile that pushes up to 20 us after its march (8 to 128 stores into the
+  // neighbour, a few at a time), a tile of the top chunk by the three planes it loads for the step outside the loop.  The
+  // walk over the grid (x fastest, then y, then z) must not END with them, or the whole kernel ends that much later
+  // (measured at 2 ranks cut along y: 12 us per iteration, with 3 % of the tiles on the faces).  So: the top row of tiles
+  // first, then row 0, 1, ...; the last strip first; and z from the middle, which also keeps the z-face tiles out of the
+  // first wave, where every boundary tile waits for the neighbour rank's kernel to start.
+  static const int rot = env_int("SB_FUSED_ROTATE", 1);
+  if (rot) {
+    s.xrot = tiles_x - 1;
+    s.yrot = tiles_y - 1;
+    s.zrot = tiles_z / 2;
   }
+  if (!any_push && !dense_ghosts) // every face is a periodic self-neighbour read in place (one GPU)
+    jacobi_fused_kernel<T, VX, SHIFT, 1><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
+  else
+    jacobi_fused_kernel<T, VX, SHIFT, 2><<<(unsigned)blocks, 256, 0, stream>>>(p, s, tiles_x, tiles_y, tiles_z);
   return 1;
 }
 
@@ -965,6 +967,7 @@ int launch_jacobi_fused(const JacobiParams &p_in, const FusedSync &sync_in, int 
     if (dbg & 1) sync.wait_row[f] = nullptr;
     if (dbg & 2) sync.signal_row[f] = nullptr;
   }
+  sync.debug = dbg;
   bool shift = false;
   const int vx = pick_vectors(p, dtype_size, allow_shift != 0, &shift);
   // x wrap (periodic self-neighbour read in place) works through the edge lanes' scalar load, so the first compute cell
