@@ -36,6 +36,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--size", type=int, default=512, help="per-GPU cube edge (BASELINE: 512)")
     p.add_argument("--dtype", default="f64", choices=["f32", "f64"])
+    p.add_argument("--grow", default="yz", choices=["yz", "cube", "x"], help="which axes the weak-scaling rule grows (see grown_size)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-overlap", action="store_true")
@@ -284,6 +285,29 @@ def halo_exchange_metric(rank, world, gpus, ngpu, iters=30):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def grown_size(n, ngpu, grow):
+    """The global size for `ngpu` subdomains of n^3.
+    --grow yz (default): the weak-scaling rule of bin/jacobi3d.cu:189-199 -- multiply the prime factors of the subdomain
+        count into the currently smallest axis -- restricted to the two slow axes (ties to z): x, the contiguous axis,
+        whose faces are single cells one row pitch apart, is never cut.  1 / 2 / 4 / 8 GPUs: 512^3, 512x512x1024,
+        512x1024x1024, 512x1024x2048 (partition 1x2x4).
+    --grow cube: the rule on all three axes with ties to z first (8 GPUs: 1024^3, partition 2x2x2);
+    --grow x: the reference's literal order, ties to x first (the same shapes as `cube`, mirrored)."""
+    from stencil_b200.domain import prime_factors
+    from stencil_b200.jacobi import scaled_size
+
+    if grow == "yz":
+        y = z = n
+        for pf in prime_factors(ngpu):
+            if z <= y:
+                z *= pf
+            else:
+                y *= pf
+        return n, y, z
+    X, Y, Z = scaled_size(n, n, n, ngpu)
+    return (Z, Y, X) if grow == "cube" else (X, Y, Z)
+
+
 def run_ours(args, rank, world):
     import torch
     import torch.distributed as td
@@ -304,12 +328,10 @@ def run_ours(args, rank, world):
         gpus = list(range(ngpu))  # one process driving N GPUs (the reference's 1 rank x N GPUs mode)
     else:
         gpus = [local]
-    X, Y, Z = scaled_size(n, n, n, ngpu)
-    cut = os.environ.get("SB_BENCH_CUT", "")  # diagnostics: which axis the weak-scaling rule grows first (default x, as the reference)
-    if cut == "y":
-        X, Y, Z = Z, X, Y
-    elif cut == "z":
-        X, Y, Z = Y, Z, X
+    X, Y, Z = grown_size(n, ngpu, args.grow)
+    cut = os.environ.get("SB_BENCH_CUT", "")  # diagnostics: one cut along a chosen axis at 2 ranks
+    if cut:
+        X, Y, Z = {"x": (2 * n, n, n), "y": (n, 2 * n, n), "z": (n, n, 2 * n)}[cut] if ngpu == 2 else (X, Y, Z)
 
     dd = sb.DistributedDomain(X, Y, Z)
     dd.set_gpus(gpus)
@@ -497,7 +519,7 @@ def run_ours(args, rank, world):
             "per_gpu": value / ngpu,
             "wall_ms_per_step": wall_ms / args.steps,
             "config": {
-                "workload": f"jacobi3d {n}^3 per GPU radius-1 {args.dtype.upper()} (BASELINE configs[1]); global {X}x{Y}x{Z}",
+                "workload": f"jacobi3d {n}^3 per GPU radius-1 {args.dtype.upper()} (BASELINE configs[1]); global {X}x{Y}x{Z} (weak-scaling rule of bin/jacobi3d.cu:189-199, --grow {args.grow})",
                 "parallelism": f"{world} process(es) x {len(gpus)} GPU(s), 3-D domain decomposition, fused P2P halo write",
                 "overlap": jac.overlap,
                 "schedule": schedule,
@@ -526,7 +548,7 @@ def run_ours(args, rank, world):
         from jacobi_parity import check_jacobi_parity
 
         kinds = {"fused": ("fused",) * 6 + ("queued",) * 2, "queued": ("queued",) * 6 + ("host-sync",) * 2, "host-sync": ("host-sync",) * 4}[schedule]
-        parity = check_jacobi_parity(scaled_size(128, 128, 128, ngpu), gpus, dtype, kinds, world)
+        parity = check_jacobi_parity(grown_size(128, ngpu, args.grow), gpus, dtype, kinds, world)
 
     xchg = None
     if not args.no_exchange_bench:
