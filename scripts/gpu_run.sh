@@ -50,8 +50,6 @@ for stage in "$@"; do
     bench default --steps 30 --warmup 5 ;;
   bench_quick)
     bench quick --steps 30 --warmup 5 --no-cpu-baseline --no-e2e ;;
-  bench_orders) # block order of the fused kernel: natural / boundary first / boundary last
-    for o in 0 1 2; do SB_FUSED_ORDER=$o bench "order$o" --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity; done ;;
   bench_f32)
     bench f32 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --dtype f32 ;;
   bench_queued)
@@ -108,8 +106,10 @@ for stage in "$@"; do
   ncu_astaroth) # the astaroth substep kernels, FP64 256^3 (variant in SB_AC_VARIANTS, default "team tile")
     SKIP_CELL=1 SKIP_ITER=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ac_t -c 6 -o "$F/prof_astaroth_f64" -f python scripts/time_astaroth.py 256 f64 1 >"$F/ncu_astaroth.log" 2>&1
     tail -3 "$F/ncu_astaroth.log" ;;
-  sanitize) # memcheck on the small fused cases
-    timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_jacobi.py -q -m gpu -x -k "block_orders and float64" 2>&1 | tail -15 | tee "$F/sanitize.txt" ;;
+  sanitize) # memcheck on the small jacobi cases (plain, regions, fused, in-process multi-subdomain)
+    timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_jacobi.py -q -m gpu -k "not full_size and not golden" >"$F/sanitize_full.txt" 2>&1
+    grep -E "ERROR SUMMARY|passed|failed|Invalid|Error" "$F/sanitize_full.txt" | sort | uniq -c | sort -rn | head -12 | tee "$F/sanitize.txt"
+    grep -E "Invalid" -A 12 "$F/sanitize_full.txt" | head -40 | cut -c1-200 ;;
   cpp) # the C++ API: the reference's own suites and drivers against our library
     ( timeout 600 bin/test_cuda 2>&1 | tail -3 ) | tee "$F/test_cuda.txt"
     ( timeout 300 bin/test_cpu 2>&1 | tail -3 ) | tee "$F/test_cpu.txt" ;;

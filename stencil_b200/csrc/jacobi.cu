@@ -120,10 +120,14 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
     return;
   }
 
-  // does this lane's vector lie inside the allocation row?  (SHIFT: a vector may hang over either end
-  // of its row into the neighbouring row of the same allocation -- valid memory, masked cells)
-  const bool xin = SHIFT ? true : (x + VX <= p.raw[0]);
-  const int xs = xin ? x : (p.x0a >= 0 ? p.x0a : p.x0a + VX); // out-of-row lanes read (and discard) an aligned in-row vector
+  // does this lane's vector lie inside the allocation row?
+  // SHIFT: a vector may hang over either end of its row into the neighbouring row of the same allocation.  That is valid
+  // memory for every vector that holds a compute cell or the ghost cell next to one (rows 1 .. ny of planes 0 .. nz+1 have a
+  // row before and after them); lanes further out -- rows much shorter than a strip put them several rows beyond the last
+  // row of the allocation -- read (and discard) an aligned vector inside the row instead.
+  const bool xin = SHIFT ? (x + VX >= p.lo[0] && x <= p.hi[0]) : (x + VX <= p.raw[0]);
+  const int xsafe = SHIFT ? (p.x0a - shift + VX) : (p.x0a >= 0 ? p.x0a : p.x0a + VX);
+  const int xs = xin ? x : xsafe;
   const long long xoff = (long long)xs * (long long)sizeof(T);
 
   // row byte offsets inside a plane; rows beyond the allocation are clamped (their results are masked)
@@ -802,8 +806,7 @@ template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p
   // (measured at 2 ranks cut along y: 12 us per iteration, with 3 % of the tiles on the faces).  So: the top row of tiles
   // first, then row 0, 1, ...; the last strip first; and z from the middle, which also keeps the z-face tiles out of the
   // first wave, where every boundary tile waits for the neighbour rank's kernel to start.
-  static const int rot = env_int("SB_FUSED_ROTATE", 1);
-  if (rot) {
+  if (env_int("SB_FUSED_ROTATE", 1)) {
     s.xrot = tiles_x - 1;
     s.yrot = tiles_y - 1;
     s.zrot = tiles_z / 2;

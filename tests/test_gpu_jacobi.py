@@ -241,16 +241,17 @@ def test_step_async_is_bitwise_step(dtype, ndom):
     assert float(np.ptp(fields[0][0])) > 0  # the hot/cold spheres made the field non-trivial
 
 
-@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("rotate", [0, 1])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_fused_kernel_block_orders(monkeypatch, order, dtype):
-    """jacobi_fused_kernel remaps the block index so that the boundary CTAs run first (1) or last (2); inner CTAs take the
-    plain loop, boundary CTAs the push loop.  Every order, on shapes with 1..N tiles per axis (also fewer than the two
-    boundary tiles), must reproduce Jacobi3D.step bit for bit."""
+def test_fused_kernel_tile_walks(monkeypatch, rotate, dtype):
+    """jacobi_fused_kernel walks its tiles from a rotated origin on every axis (SB_FUSED_ROTATE, default on) so that the
+    walk does not end with tiles that push; inner tiles take the plain loop, boundary tiles the variant their faces need.
+    Either walk, on shapes with 1..N tiles per axis (also fewer than the two boundary tiles, partial tiles, one-plane
+    chunks), must reproduce Jacobi3D.step bit for bit."""
     from stencil_b200.jacobi import Jacobi3D, jacobi_radius
 
-    monkeypatch.setenv("SB_FUSED_ORDER", str(order))
-    for size, ndom in [((40, 24, 70), 1), ((200, 20, 40), 1), ((256, 40, 100), 1), ((384, 30, 66), 2), ((130, 17, 33), 1)]:
+    monkeypatch.setenv("SB_FUSED_ROTATE", str(rotate))
+    for size, ndom in [((40, 24, 70), 1), ((200, 20, 40), 1), ((256, 40, 100), 1), ((384, 30, 66), 2), ((130, 17, 33), 1), ((64, 40, 65), 2), ((128, 7, 1), 1)]:
         fields = []
         for mode in ("sync", "fused"):
             dd = sb.DistributedDomain(*size)
