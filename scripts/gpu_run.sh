@@ -76,6 +76,8 @@ for stage in "$@"; do
   bench_rot) # the rotated walk over the tiles, on and off
     SB_FUSED_ROTATE=0 bench rot0 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity
     SB_FUSED_ROTATE=1 bench rot1 --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity ;;
+  time_f32) # FP32 fused kernel variants on one GPU
+    DTYPE=f32 F32VARIANTS=1 timeout 600 python scripts/time_fused.py 512 30 2>&1 | tail -14 | tee "$F/time_f32.txt" ;;
   time_fused) # kernel variants + single-GPU stand-ins for the multi-rank kernels, one box
     timeout 900 python scripts/time_fused.py 512 30 2>&1 | tail -24 | tee "$F/time_fused.txt" ;;
   ncu_fused2) # the fused kernel of the 2-subdomain stand-in (half of its CTAs are boundary CTAs) under ncu
@@ -103,6 +105,9 @@ for stage in "$@"; do
   ncu_fused)
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:jacobi_fused_kernel -s 4 -c 1 -o "$F/prof_jacobi_fused" -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity >"$F/ncu_full.log" 2>&1
     tail -3 "$F/ncu_full.log" ;;
+  ncu_fused_f32)
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:jacobi_fused_kernel -s 4 -c 1 -o "$F/prof_jacobi_fused_f32" -f python bench.py --dtype f32 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-exchange-bench --no-parity >"$F/ncu_full_f32.log" 2>&1
+    tail -3 "$F/ncu_full_f32.log" ;;
   ncu_astaroth) # the astaroth substep kernels, FP64 256^3 (variant in SB_AC_VARIANTS, default "team tile")
     SKIP_CELL=1 SKIP_ITER=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ac_t -c 6 -o "$F/prof_astaroth_f64" -f python scripts/time_astaroth.py 256 f64 1 >"$F/ncu_astaroth.log" 2>&1
     tail -3 "$F/ncu_astaroth.log" ;;

@@ -139,9 +139,10 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   const bool edge_lane = (lane == 0) || (lane == 31);
   long long phstep = S; // per-plane advance of ph (XPUSH: a dense x-ghost array is z fastest)
   int hxv = lane == 0 ? x - 1 : x + VX;
+  bool far = false; // this lane's edge scalar / patched element comes from the other end of the row
   if (EDGE && p.xwrap) { // periodic self-neighbour: the cell beyond a face is the first / last cell of the same row
-    if (hxv == p.lo[0] - 1) hxv = p.hi[0] - 1;
-    else if (hxv == p.hi[0]) hxv = p.lo[0];
+    if (hxv == p.lo[0] - 1) hxv = p.hi[0] - 1, far = edge_lane;
+    else if (hxv == p.hi[0]) hxv = p.lo[0], far = edge_lane;
   }
   const int hx = clampi(hxv, 0, p.raw[0] - 1);
 #pragma unroll
@@ -167,25 +168,25 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
 
   // SHIFT + periodic self-neighbour along x: on phase-shifted rows the ghost cell just outside a face sits INSIDE a lane's
   // vector (the strip starts VX / 2 cells early), where the edge lanes' scalar cannot replace it: that element is patched
-  // at load time with the cell of the opposite face (one predicated scalar load per step for two lanes of such a row)
+  // with the cell of the opposite face.  A ghost cell only matters as the x neighbour of a compute cell, i.e. while its
+  // vector is the CURRENT plane, so the scalar loaded beside plane z+1's vector is selected in one step later, when it has
+  // long arrived.  (Selected into plane z+1 right away, the select made the warp wait for that plane before it had even
+  // asked for the rows above and below: two memory latencies per step, the x-face tiles of FP32 512^3 ran at half speed.)
+  // Every lane loads a scalar (its own first element where nothing is patched): no divergent branch around a load.
   int wrap_i = -1;
-  const char *wrap_p = nullptr; // the wrapped cell of plane z+1
-  if (EDGE && SHIFT && p.xwrap) {
+  const bool xpatch = EDGE && SHIFT && p.xwrap && !(debug & 131072); // kernel-uniform (131072: experiment, no patch at all)
+  const char *wrap_p = xpatch ? pc[0] : nullptr; // the scalar of plane z+1
+  if (xpatch) {
 #pragma unroll
     for (int i = 0; i < VX; ++i) {
       const int xi = x + i;
       const int xw = xi == p.lo[0] - 1 ? p.hi[0] - 1 : (xi == p.hi[0] ? p.lo[0] : -1);
       if (xw >= 0) wrap_i = i, wrap_p = src + (long long)(z0 + 1) * S + yo(y) + (long long)xw * (long long)sizeof(T);
     }
+    if (debug & 65536) wrap_p = pc[0]; // experiment: the patch scalar from the lane's own vector (wrong halos)
   }
-  auto patch = [&](V &v, long long planes_back) {
-    if (EDGE && SHIFT && wrap_i >= 0) {
-      const T w = *reinterpret_cast<const T *>(wrap_p - planes_back * S);
-#pragma unroll
-      for (int i = 0; i < VX; ++i)
-        if (wrap_i == i) v.v[i] = w;
-    }
-  };
+  T wA = T(0), wB = T(0), wC = T(0); // the scalar that belongs into each register plane's vector (loaded with it; no copies:
+                                     // a copy right behind the load would make the warp wait for it)
   const long long zspan = (long long)(p.hi[2] - p.lo[2]) * S; // a periodic self-neighbour along z is this many bytes away
 
   // store masks
@@ -249,17 +250,19 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
 
   // one plane: load z+1, compute z from (z-1, z, z+1), store, advance every running pointer.  ZP (the two steps outside the
   // loop): also store the result into the z neighbours named by zmask (bit 0: -z, bit 1: +z).
-  auto step = [&](auto zp_tag, const unsigned zmask, const V(&prev)[RY], const V(&cur)[RY], V(&nxt)[RY]) {
+  auto step = [&](auto zp_tag, const unsigned zmask, const V(&prev)[RY], const V(&cur)[RY], V(&nxt)[RY], const T &wcur, T &wnext) {
     constexpr bool ZP = decltype(zp_tag)::value;
+    if (xpatch && wrap_i >= 0) wnext = *reinterpret_cast<const T *>(wrap_p);
 #pragma unroll
     for (int j = 0; j < RY; ++j) nxt[j] = *reinterpret_cast<const V *>(pc[j]);
-    if (EDGE && SHIFT) {
-      patch(nxt[0], 0);
-      wrap_p += S;
-    }
+    if (EDGE && SHIFT) wrap_p += S;
     if (p.prefetch > 0 && z + 1 + p.prefetch <= zlast) {
 #pragma unroll
       for (int j = 0; j < RY; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc[j] + (long long)p.prefetch * S));
+      // cells read from the other end of the row are in nobody's prefetch stream here: without this every step of an
+      // x-face warp waits for DRAM (FP32 512^3, one GPU: 0.290 -> ms per iteration)
+      if (EDGE && far) asm volatile("prefetch.global.L2 [%0];" ::"l"(ph[0] + (long long)p.prefetch * S));
+      if (EDGE && SHIFT && wrap_i >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(wrap_p + (long long)(p.prefetch - 1) * S)); // (wrap_p is already one plane on)
     }
     V up, dn;
     if (SHIFT) { // the rows above / below have the other phase: two aligned half vectors each
@@ -279,19 +282,31 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
     }
     const int dzv = z + p.org[2] - p.cz;
     const int dz2 = dzv * dzv;
+    T hh[RY];
 #pragma unroll
     for (int j = 0; j < RY; ++j) {
-      T h = T(0);
-      if (edge_lane) h = *reinterpret_cast<const T *>(ph[j]);
-      T left = __shfl_up_sync(0xffffffffu, cur[j].v[VX - 1], 1);
-      T right = __shfl_down_sync(0xffffffffu, cur[j].v[0], 1);
+      hh[j] = T(0);
+      if (edge_lane) hh[j] = *reinterpret_cast<const T *>(ph[j]);
+    }
+    V cc[RY]; // the current plane as the x direction sees it
+#pragma unroll
+    for (int j = 0; j < RY; ++j) cc[j] = cur[j];
+    if (EDGE && SHIFT && xpatch) {
+#pragma unroll
+      for (int i = 0; i < VX; ++i) cc[0].v[i] = (wrap_i == i) ? wcur : cc[0].v[i];
+    }
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      const T h = hh[j];
+      T left = __shfl_up_sync(0xffffffffu, cc[j].v[VX - 1], 1);
+      T right = __shfl_down_sync(0xffffffffu, cc[j].v[0], 1);
       if (lane == 0) left = h;
       if (lane == 31) right = h;
       V out;
 #pragma unroll
       for (int i = 0; i < VX; ++i) {
-        const T px = (i < VX - 1) ? cur[j].v[i + 1 < VX ? i + 1 : i] : right;
-        const T mx = (i > 0) ? cur[j].v[i > 0 ? i - 1 : 0] : left;
+        const T px = (i < VX - 1) ? cc[j].v[i + 1 < VX ? i + 1 : i] : right;
+        const T mx = (i > 0) ? cc[j].v[i > 0 ? i - 1 : 0] : left;
         const T py = (j < RY - 1) ? cur[j + 1 < RY ? j + 1 : j].v[i] : dn.v[i];
         const T my = (j > 0) ? cur[j > 0 ? j - 1 : 0].v[i] : up.v[i];
         out.v[i] = stencil_value<T>(px, mx, py, my, nxt[j].v[i], prev[j].v[i]);
@@ -361,13 +376,12 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
       if (below) pa += zspan;
       A[j] = *reinterpret_cast<const V *>(pa);
       B[j] = *reinterpret_cast<const V *>(pc[j] - S);
-      patch(A[j], below ? 2 - (long long)(p.hi[2] - p.lo[2]) : 2);
-      patch(B[j], 1);
       if (p.zwrap) pc[j] -= zspan;
     }
+    if (xpatch && wrap_i >= 0) wB = *reinterpret_cast<const T *>(wrap_p - S);
     if (SHIFT && p.zwrap) wrap_p -= zspan;
     const unsigned zmask = (p.push_ptr[5] && !(z0 == p.lo[2] && p.push_ptr[4])) ? 2u : 0u; // (on both z faces: finish_tile copies)
-    step(WithZ{}, zmask, A, B, C);
+    step(WithZ{}, zmask, A, B, C, wB, wC);
     const long long back = (long long)(up + 1) * S;
 #pragma unroll
     for (int j = 0; j < RY; ++j) {
@@ -392,21 +406,21 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
       if (below) pa += zspan;
       A[j] = *reinterpret_cast<const V *>(pa);
       B[j] = *reinterpret_cast<const V *>(pc[j] - S); // plane z0
-      patch(A[j], below ? 2 - (long long)(p.hi[2] - p.lo[2]) : 2);
-      patch(B[j], 1);
     }
+    if (xpatch && wrap_i >= 0) wB = *reinterpret_cast<const T *>(wrap_p - S);
     if (EDGE && z0 == p.lo[2] && p.push_ptr[4] && !(z1 == p.hi[2] && p.push_ptr[5])) { // the first plane of the bottom chunk is parked for the -z neighbour
-      step(WithZ{}, 1u, A, B, C);
+      step(WithZ{}, 1u, A, B, C, wB, wC);
 #pragma unroll
       for (int j = 0; j < RY; ++j) A[j] = B[j], B[j] = C[j];
+      wB = wC;
     }
   }
   while (z < zend) {
-    step(NoZ{}, 0u, A, B, C);
+    step(NoZ{}, 0u, A, B, C, wB, wC);
     if (z >= zend) break;
-    step(NoZ{}, 0u, B, C, A);
+    step(NoZ{}, 0u, B, C, A, wC, wA);
     if (z >= zend) break;
-    step(NoZ{}, 0u, C, A, B);
+    step(NoZ{}, 0u, C, A, B, wA, wB);
   }
 }
 
@@ -416,6 +430,88 @@ __global__ void __launch_bounds__(256, MB) jacobi_march_kernel(const __grid_cons
   const int bx = b % tiles_x;
   b /= tiles_x;
   march_body<T, VX, RY, SHIFT, 0>(p, bx, b % tiles_y, b / tiles_y);
+}
+
+// The tail column of phase-shifted rows (fused kernel).  FP32 rows of 514 floats alternate between two 16-byte phases, so
+// 512 compute cells starting at cell 1 touch 129 aligned vectors of every row: four strips of 32 lanes and one vector
+// more, with 1 or 3 compute cells in it.  As a fifth strip that vector costs a whole warp per row and step (a fifth of all
+// warps of the launch, and two more strips of every row count as x-face tiles).  Here it is a tile of its own kind: one
+// THREAD per row, 256 rows per CTA, marching the same z chunk with the planes z-1 / z / z+1 of its vector in registers,
+// the neighbours in x and y as scalar loads (L2: the main strips fetch the same sectors).  It reads periodic
+// self-neighbours in place and stores its cells of the y / z faces into the neighbours itself, step by step (a handful
+// of stores per tile).  Not used when the +x face must be pushed (the launcher then keeps the fifth strip).
+template <typename T, int VX>
+__device__ __forceinline__ void march_column(const JacobiParams &p, const int xcol, const int cy, const int bz, const bool wait_barrier) {
+  using V = Vec<T, VX>;
+  const long long S = p.slice, P = p.pitch, es = (long long)sizeof(T);
+  const int y = p.lo[1] + cy * 256 + (int)threadIdx.x;
+  const int z0 = p.lo[2] + bz * p.zchunk;
+  const int z1 = min(z0 + p.zchunk, p.hi[2]);
+  if (wait_barrier) __syncthreads();
+  if (y >= p.hi[1]) return;
+  const int shift = (int)((((unsigned long long)y * (unsigned long long)P) & (sizeof(T) * VX - 1)) / sizeof(T));
+  const int xv = xcol - shift;              // first cell of this row's tail vector (16-byte aligned; >= lo: there are main strips)
+  const int n = min(p.hi[0] - xv, VX);      // compute cells in it (1 .. VX)
+  int yu = y - 1, yd = y + 1;
+  if (p.ywrap) {
+    if (yu == p.lo[1] - 1) yu = p.hi[1] - 1;
+    if (yd == p.hi[1]) yd = p.lo[1];
+  }
+  const int xr = p.xwrap ? p.lo[0] : p.hi[0]; // the cell beyond the +x face: the ghost cell, or this row's first cell
+  const char *row = p.src + (long long)y * P, *rowu = p.src + (long long)yu * P, *rowd = p.src + (long long)yd * P;
+  char *orow = p.dst + (long long)y * P;
+  auto plane = [&](int zz) { // byte offset of plane zz, a periodic self-neighbour along z read in place
+    if (p.zwrap) {
+      if (zz == p.lo[2] - 1) zz = p.hi[2] - 1;
+      else if (zz == p.hi[2]) zz = p.lo[2];
+    }
+    return (long long)zz * S;
+  };
+  const int rr = (p.rad + 1) * (p.rad + 1);
+  const int dyv = y + p.org[1] - p.cy;
+  const int dy2 = dyv * dyv;
+  const int gx0 = xv + p.org[0];
+  char *ypush = (y == p.lo[1] && p.push_ptr[2]) ? p.push_ptr[2] : nullptr; // this row is a y face of the subdomain
+  long long yslice = p.push_slice[2];
+  if (y == p.hi[1] - 1 && p.push_ptr[3] && !ypush) ypush = p.push_ptr[3], yslice = p.push_slice[3];
+  char *ypush2 = (y == p.hi[1] - 1 && p.push_ptr[3] && ypush != p.push_ptr[3]) ? p.push_ptr[3] : nullptr; // a one-row subdomain: both
+
+  V prev = *reinterpret_cast<const V *>(row + plane(z0 - 1) + (long long)xv * es);
+  V cur = *reinterpret_cast<const V *>(row + (long long)z0 * S + (long long)xv * es);
+  for (int z = z0; z < z1; ++z) {
+    const V nxt = *reinterpret_cast<const V *>(row + plane(z + 1) + (long long)xv * es);
+    const long long pz = (long long)z * S;
+    const T left = *reinterpret_cast<const T *>(row + pz + (long long)(xv - 1) * es);
+    const T right = *reinterpret_cast<const T *>(row + pz + (long long)xr * es);
+    const int dzv = z + p.org[2] - p.cz;
+    const int dyz2 = dy2 + dzv * dzv;
+#pragma unroll
+    for (int i = 0; i < VX; ++i) {
+      if (i >= n) continue;
+      const long long xo = (long long)(xv + i) * es;
+      const T px = (i + 1 < VX && i + 1 < n) ? cur.v[i + 1 < VX ? i + 1 : i] : right;
+      const T mx = (i > 0) ? cur.v[i > 0 ? i - 1 : 0] : left;
+      const T py = *reinterpret_cast<const T *>(rowd + pz + xo);
+      const T my = *reinterpret_cast<const T *>(rowu + pz + xo);
+      T out = stencil_value<T>(px, mx, py, my, nxt.v[i], prev.v[i]);
+      if (dyz2 < rr) {
+        const int dh = (gx0 + i - p.hot_x) * (gx0 + i - p.hot_x) + dyz2;
+        const int dc = (gx0 + i - p.cold_x) * (gx0 + i - p.cold_x) + dyz2;
+        if (in_sphere(dh, p.rad)) {
+          out = T(1);
+        } else if (in_sphere(dc, p.rad)) {
+          out = T(0);
+        }
+      }
+      *reinterpret_cast<T *>(orow + pz + xo) = out;
+      if (ypush) *reinterpret_cast<T *>(ypush + xo + (long long)z * yslice) = out;
+      if (ypush2) *reinterpret_cast<T *>(ypush2 + xo + (long long)z * p.push_slice[3]) = out;
+      if (z == p.lo[2] && p.push_ptr[4]) *reinterpret_cast<T *>(p.push_ptr[4] + (long long)y * p.push_pitch[4] + xo) = out;
+      if (z == p.hi[2] - 1 && p.push_ptr[5]) *reinterpret_cast<T *>(p.push_ptr[5] + (long long)y * p.push_pitch[5] + xo) = out;
+    }
+    prev = cur;
+    cur = nxt;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------- fused iteration
@@ -456,6 +552,35 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
   // made all its stores visible; nothing of this kernel is outstanding yet, so the release costs nothing).
   if (EDGE >= 2 && s.any_signal && b == 0 && threadIdx.x < 6 && s.signal_row[threadIdx.x])
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(s.signal_row[threadIdx.x]), "r"(s.signal_value) : "memory");
+  if (SHIFT && s.col_cy) { // the first CTAs of the launch are the tail-column tiles (march_column)
+    const int ncol = s.col_cy * nz;
+    if (b < ncol) {
+      const int cy = b % s.col_cy;
+      int cz = b / s.col_cy + s.zrot;
+      if (cz >= nz) cz -= nz;
+      unsigned cf = 0; // faces of the subdomain this tile pushes to (x: none, see launch_fused)
+      if (cy == 0 && p.push_ptr[2]) cf |= 4u;
+      if (cy == s.col_cy - 1 && p.push_ptr[3]) cf |= 8u;
+      if (cz == 0 && p.push_ptr[4]) cf |= 16u;
+      if (cz == nz - 1 && p.push_ptr[5]) cf |= 32u;
+      const bool cw = s.any_wait && cf;
+      if (cw && threadIdx.x == 0) {
+#pragma unroll
+        for (int f = 2; f < 6; ++f)
+          if ((cf >> f & 1u) && s.wait_row[f]) {
+            uint32_t v;
+            while (true) {
+              asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(s.wait_row[f]) : "memory");
+              if ((int32_t)(v - s.wait_value) >= 0) break;
+              __nanosleep(100);
+            }
+          }
+      }
+      march_column<T, VX>(p, s.col_x, cy, cz, cw);
+      return;
+    }
+    b -= ncol;
+  }
   int bx = b % nx + s.xrot;
   b /= nx;
   int by = b % ny + s.yrot;
@@ -465,7 +590,7 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
   if (bz >= nz) bz -= nz;
   // the faces this CTA's cells lie on (phase-shifted rows end one strip later than the others, so with SHIFT the last TWO
   // strips along x may hold cells of the +x face)
-  const int nxhi = SHIFT ? min(nx, 2) : 1;
+  const int nxhi = SHIFT ? (s.col_cy ? 0 : min(nx, 2)) : 1; // (with tail-column tiles no strip holds a cell of the +x face)
   unsigned touch = 0;
   if (bx == 0) touch |= 1u;
   if (bx >= nx - nxhi) touch |= 2u;
@@ -473,6 +598,7 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
   if (by == ny - 1) touch |= 8u;
   if (bz == 0) touch |= 16u;
   if (bz == nz - 1) touch |= 32u;
+  if (s.debug & 64) touch &= (unsigned)(s.debug >> 8); // experiment: only tiles on the faces in bits 8.. run a boundary variant (wrong halos)
   if (!touch) { // CTAs that touch no face take the plain loop
     march_body<T, VX, 1, SHIFT, 0>(p, bx, by, bz);
     return;
@@ -512,7 +638,7 @@ __device__ __forceinline__ void fused_body(const JacobiParams &p, const FusedSyn
   else if (needx)
     march_body<T, VX, 1, SHIFT, 3>(p, bx, by, bz, waits, s.debug);
   else
-    march_body<T, VX, 1, SHIFT, 1>(p, bx, by, bz, waits);
+    march_body<T, VX, 1, SHIFT, 1>(p, bx, by, bz, waits, s.debug);
   if (EDGE >= 2) finish_tile<T, VX, SHIFT>(p, s, nx, ny, nz);
 }
 
@@ -529,6 +655,7 @@ template <typename T, int VX, bool SHIFT> __device__ __noinline__ void finish_ti
   int b, tid;
   asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(b));
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+  if (SHIFT && s.col_cy) b -= s.col_cy * nz; // (tail-column tiles never come here)
   int bx = b % nx + s.xrot;
   b /= nx;
   int by = b % ny + s.yrot;
@@ -785,12 +912,24 @@ int env_int(const char *name, int dflt);
 
 template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p, FusedSync s, cudaStream_t stream) {
   const int x0a = p.x0a;
-  const int tiles_x = (p.hi[0] - x0a + (SHIFT ? VX / 2 : 0) + 32 * VX - 1) / (32 * VX);
+  int tiles_x = (p.hi[0] - x0a + (SHIFT ? VX / 2 : 0) + 32 * VX - 1) / (32 * VX);
   const int ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
   const int tiles_z = (nz + p.zchunk - 1) / p.zchunk;
   const int tiles_y = (ny + 7) / 8;
   if ((long long)tiles_z * tiles_y > kMaxGroups || (long long)tiles_z * tiles_x > kMaxGroups || (long long)tiles_y * tiles_x > kMaxGroups) return -2;
-  const long long blocks = (long long)tiles_x * tiles_y * tiles_z;
+  // Phase-shifted rows whose last strip holds at most one vector of compute cells (FP32 512^3: 1 or 3 cells per row): that
+  // vector becomes tail-column tiles (march_column), the strips before it the main grid.  Not when the +x face is pushed:
+  // its cells would have to be parked by the column tiles.
+  s.col_cy = s.col_x = 0;
+  if (SHIFT && tiles_x >= 2 && !p.push_ptr[1] && env_int("SB_JACOBI_COLUMN", 1)) {
+    const int xcol = x0a + (tiles_x - 1) * 32 * VX; // first cell of the last strip on rows of phase 0
+    if (p.hi[0] - (xcol - VX / 2) <= VX && xcol - VX / 2 >= p.lo[0]) {
+      s.col_cy = (ny + 255) / 256;
+      s.col_x = xcol;
+      tiles_x -= 1;
+    }
+  }
+  const long long blocks = (long long)tiles_x * tiles_y * tiles_z + (long long)s.col_cy * tiles_z;
   s.xrot = s.yrot = s.zrot = 0;
   s.any_wait = s.any_signal = 0;
   for (int f = 0; f < 6; ++f) {
@@ -800,12 +939,10 @@ template <typename T, int VX, bool SHIFT> int launch_fused(const JacobiParams &p
   const bool dense_ghosts = p.xghost_ptr[0] || p.xghost_ptr[1];
   bool any_push = false;
   for (int f = 0; f < 6; ++f) any_push = any_push || p.push_ptr[f];
-  // Boundary tiles stay longer than inner ones -- a tile that pushes up to 20 us after its march (8 to 128 stores into the
-  // neighbour, a few at a time), a tile of the top chunk by the three planes it loads for the step outside the loop.  The
-  // walk over the grid (x fastest, then y, then z) must not END with them, or the whole kernel ends that much later
-  // (measured at 2 ranks cut along y: 12 us per iteration, with 3 % of the tiles on the faces).  So: the top row of tiles
-  // first, then row 0, 1, ...; the last strip first; and z from the middle, which also keeps the z-face tiles out of the
-  // first wave, where every boundary tile waits for the neighbour rank's kernel to start.
+  // The walk over the tiles (x fastest, then y, then z) starts at a rotated origin: boundary tiles stay longer than inner
+  // ones (pushes after the march, three extra plane loads in the top chunk), so the walk should not end with them, and z
+  // starts in the middle, which keeps the z-face tiles out of the first wave, where every boundary tile waits for the
+  // neighbour rank's kernel to start.  (Measured on and off, one and two ranks: within the run-to-run noise.)
   if (env_int("SB_FUSED_ROTATE", 1)) {
     s.xrot = tiles_x - 1;
     s.yrot = tiles_y - 1;
@@ -958,9 +1095,9 @@ int launch_jacobi_fused(const JacobiParams &p_in, const FusedSync &sync_in, int 
   JacobiParams p = p_in;
   const int ex = p.hi[0] - p.lo[0], ey = p.hi[1] - p.lo[1], ez = p.hi[2] - p.lo[2];
   if (ex <= 0 || ey <= 0 || ez <= 0) return 0;
-  static const int zchunk_env = env_int("SB_JACOBI_ZCHUNK", 0);
-  static const int pf = env_int("SB_JACOBI_PREFETCH", 2);
-  static const int allow_shift = env_int("SB_JACOBI_SHIFT", 1);
+  const int zchunk_env = env_int("SB_JACOBI_ZCHUNK", 0);
+  const int pf = env_int("SB_JACOBI_PREFETCH", 2);
+  const int allow_shift = env_int("SB_JACOBI_SHIFT", 1);
   p.zchunk = (zchunk_env > 0 && zchunk_env <= 32) ? zchunk_env : 32; // the x faces are staged 32 planes at a time
   if (p.zchunk > ez) p.zchunk = ez;
   p.prefetch = pf;
@@ -976,8 +1113,9 @@ int launch_jacobi_fused(const JacobiParams &p_in, const FusedSync &sync_in, int 
   // x wrap (periodic self-neighbour read in place) works through the edge lanes' scalar load, so the first compute cell
   // must open lane 0 of the first strip and the last one must close lane 31 of the last strip; otherwise the ghost
   // column is read by a vector load or a shuffle and the x faces are pushed into the ghost cells like any other face
-  // (phase-shifted FP32 rows: the same conditions; there the ghost element inside a vector is patched, see march_body)
-  if (p.xwrap && !(p.x0a == p.lo[0] && (p.hi[0] - p.lo[0]) % (32 * vx) == 0)) p.xwrap = 0;
+  // (phase-shifted FP32 rows: always possible -- a ghost cell inside a vector is patched, one beside lane 0 / 31 is the
+  // edge scalar, see march_body)
+  if (p.xwrap && !shift && !(p.x0a == p.lo[0] && (p.hi[0] - p.lo[0]) % (32 * vx) == 0)) p.xwrap = 0;
   if (p.xwrap) p.push_ptr[0] = p.push_ptr[1] = nullptr;
   if (p.xghost_ptr[0] || p.xghost_ptr[1]) {
     // a dense received x array is read by the edge lanes' scalar load: same layout conditions as the wrap
