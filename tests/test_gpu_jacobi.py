@@ -251,7 +251,8 @@ def test_fused_kernel_tile_walks(monkeypatch, rotate, dtype):
     from stencil_b200.jacobi import Jacobi3D, jacobi_radius
 
     monkeypatch.setenv("SB_FUSED_ROTATE", str(rotate))
-    for size, ndom in [((40, 24, 70), 1), ((200, 20, 40), 1), ((256, 40, 100), 1), ((384, 30, 66), 2), ((130, 17, 33), 1), ((64, 40, 65), 2), ((128, 7, 1), 1)]:
+    for size, ndom in [((40, 24, 70), 1), ((200, 20, 40), 1), ((256, 40, 100), 1), ((384, 30, 66), 2), ((130, 17, 33), 1), ((64, 40, 65), 2), ((128, 7, 1), 1),
+                       ((128, 300, 40), 2), ((129, 40, 300), 2), ((256, 600, 9), 2)]:  # FP32: tail-column tiles that push y / z faces
         fields = []
         for mode in ("sync", "fused"):
             dd = sb.DistributedDomain(*size)
