@@ -79,10 +79,4 @@ if os.environ.get("SPLITS", "1") == "1":
     run(8, "fused, 8 x 512^3 cut along x, y and z NOPUSH", shape=(2 * n, 2 * n, 2 * n))
     del os.environ["SB_DEBUG_NOPUSH"]
     sys.exit(0)
-for nopush in ("", "1"):
-    if nopush:
-        os.environ["SB_DEBUG_NOPUSH"] = "1"  # timing only: nothing is shipped (results wrong)
-    for regs, split in (("64", "1"), ("64", "0"), ("56", "1")):
-        os.environ["SB_FUSED_REGS"], os.environ["SB_FUSED_SPLIT"] = regs, split
-        for ndom in (1, 2, 8):
-            run(ndom, f"fused regs={regs} split={split} subdomains={ndom}" + (" NOPUSH" if nopush else ""))
+run(1, "fused, one 512^3 subdomain (every neighbour is the subdomain itself)")
