@@ -85,13 +85,12 @@ __shared__ uint4 g_zstage[8 * 32];
 //            from the opposite face of src (pointer set-up before the loop).  The loop itself is the plain one.
 //   2 XPUSH  the x neighbour of the first / last column may come from a dense received array, and the tile's own x-face
 //            cells are parked in shared memory as the march goes (one predicated STS per step).
-//   4 YPUSH  the warp that owns a y-face row parks it in shared memory as well (one predicated STS.128 per step).  Not a
-//            store into the neighbour: measured, a warp that issues one NVLink store per step runs at NVLink latency
-//            (the y-face CTAs, 3 % of the grid, cost 10 us per iteration that way).
+//   4 YPUSH  the warp that owns a y-face row parks it in shared memory as well (one predicated STS.128 per step); stores
+//            into the neighbour never sit between two steps of the march.
 // z faces cost the loop nothing: the first plane of the bottom chunk and the last plane of the top chunk are computed by
 // two steps taken out of the loop (the top one FIRST, from three planes loaded for it alone -- 2 planes in 32 read twice by
-// 1 CTA in 16), which store their result a second time, into the neighbour, and which know about a periodic
-// self-neighbour along z (the plane beyond the top is the bottom plane).
+// 1 CTA in 16), which park their result for the neighbour as well, and which know about a periodic self-neighbour along
+// z (the plane beyond the top is the bottom plane).
 // The kernel is latency- and issue-bound at once (53 % issue utilisation with 8 warps per scheduler): every instruction
 // added to the loop shows in the run time, so each boundary CTA runs the leanest variant that serves its faces.
 template <typename T, int VX, int RY, bool SHIFT, int MODE>
@@ -209,14 +208,12 @@ __device__ __forceinline__ void march_body(const JacobiParams &p, const int bx, 
   }
   const int gx0 = x + p.org[0];
 
-  // ---- EDGE: what this warp contributes to the neighbours' halos (see jacobi_fused_kernel).  No global load is ever
-  // issued for it after the march: under a saturated memory system a dependent load costs microseconds.
-  //  x faces: the lane holding the first / last cell of the row parks it in shared memory every step (one predicated STS);
-  //           after the march the warp writes the row's chunk with one store per lane (a 256-byte line of the dense array).
-  //  y faces: the warp that owns the first / last row stores its vector a second time, into the neighbour's ghost row,
-  //           through a loop-invariant address difference (one predicated vector store per step).
-  //  z faces: the last plane of the chunk is still in registers after the loop; the first one is re-read (own store).
-  //  Everything that happens after the march is in finish_tile, which derives its own indices: nothing of it is live here.
+  // ---- What this warp contributes to the neighbours' halos (see jacobi_fused_kernel): parked in shared memory while it
+  // marches, stored into the neighbour by finish_tile -- which derives its own indices, so nothing of it is live here.
+  //  x faces: the lane holding the first / last cell of the row parks it every step (one predicated STS);
+  //  y faces: the warp that owns the first / last row parks its vector every step (one predicated STS.128);
+  //  z faces: the first plane of the bottom chunk and the last plane of the top chunk are parked by the two steps taken
+  //           out of the loop (below).
   int xsi = -1;       // which element of this lane's vector is an x-face cell (-1: none; a lane never holds both faces: ex >= 16)
   T *xsp = nullptr;   // where that cell of the current plane is parked
   uint4 *ysp = nullptr; // YPUSH: where this lane's vector of the current plane is parked (null: not a y-face row)
