@@ -151,6 +151,11 @@ def test_fused_schedule_choice_per_partition():
     assert fused_x_mode(small, owners(small, 1), 8, r, "1") == "queued"
     # FP32: strips of 128 cells, and 514-float rows alternate between two 16-byte phases
     assert fused_x_mode(two, owners(two, 1), 4, r, "1") == "queued"
+    # bench.py's default shapes grow along y and z only: x never crosses ranks, either precision runs the fused schedule
+    for size, n, dim in (((512, 512, 1024), 2, (1, 1, 2)), ((512, 1024, 1024), 4, (1, 2, 2)), ((512, 1024, 2048), 8, (1, 2, 4))):
+        part = Partition(size, r, 1, n)
+        assert tuple(part.dim) == dim
+        assert fused_x_mode(part, owners(part, 1), 8, r) == "direct" and fused_x_mode(part, owners(part, 1), 4, r) == "direct"
 
 
 def test_ctypes_structs_match_the_header(tmp_path):
