@@ -524,7 +524,7 @@ def run_ours(args, rank, world):
                 "overlap": jac.overlap,
                 "schedule": schedule,
                 "iteration_sync": {
-                    "fused": "one kernel per iteration: update + halo push into the neighbours' ghost cells; iterations ordered by CUDA events / device-side counters (Jacobi3D.step_fused)",
+                    "fused": "one kernel per iteration: update + halo push into the neighbours' ghost cells; ranks ordered inside the kernel (its first CTA publishes the iteration number to every neighbour rank, boundary tiles poll the neighbour's word), subdomains of one process by CUDA events (Jacobi3D.step_fused)",
                     "queued": "interior || exchange -> exterior, dependencies as CUDA events + ready/done flags (Jacobi3D.step_async)",
                     "host-sync": "host-side after exchange and exterior (Jacobi3D.step, the reference's loop)",
                 }[schedule],
